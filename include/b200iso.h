@@ -1,0 +1,116 @@
+/* b200iso.h -- C ABI of libb200iso.so, the B200 (sm_100a) isosurface extractor that stands behind
+ * Meshing.jl's `isosurface(sdf::AbstractArray{T,3}, method, X, Y, Z) -> (vertices, faces)`.
+ *
+ * The reference has no FFI layer: its boundary is Julia multiple dispatch on the `method` type
+ * (src/marching_cubes.jl:27, src/marching_tetrahedra.jl:129, forwarder src/isosurface.jl:30-32).
+ * This header is what a Julia shim `ccall`s instead of running those two loops (INTEGRATION.md shows
+ * the binding).  Plain pointers and sizes only; no exceptions cross the boundary; every function
+ * returns 0 on success or a negative B200ISO_E* code, with a message in b200iso_last_error().
+ *
+ * Conventions (identical to the reference):
+ *   - the field is column-major, x contiguous: sample (x,y,z) (0-based) is sdf[x + ldx*(y + ny*z)]
+ *     (Julia `sdf[x+1,y+1,z+1]`; ldx == nx for a dense Array, > nx for a padded x-slab);
+ *   - voxels are visited x-outermost, z-innermost (src/marching_cubes.jl:40,
+ *     src/marching_tetrahedra.jl:144); vertex and face order follow that scan exactly;
+ *   - vertices are xyz triples (Vector{NTuple{3,T}} layout), T = Float32 or Float64 by the
+ *     reference's promote_type rule (src/marching_cubes.jl:31, src/marching_tetrahedra.jl:131);
+ *   - faces are triples of 1-based Int64 vertex indices (Vector{NTuple{3,Int}}).
+ * The library never retains or frees caller memory.  A handle is not thread-safe; use one per thread.
+ */
+#ifndef B200ISO_H
+#define B200ISO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200iso_handle b200iso_handle;
+
+/* method type: replaces dispatch on MarchingCubes / MarchingTetrahedra (src/algorithmtypes.jl:23-40) */
+enum { B200ISO_MC = 0, B200ISO_MT = 1 };
+/* where a caller pointer lives */
+enum { B200ISO_HOST = 0, B200ISO_DEVICE = 1 };
+/* element type of the endpoints of X, Y, Z: Int (default -1:1 => LinRange{Float64} and no Float64
+ * promotion of the vertex type), Float32, Float64 (src/marching_cubes.jl:31,36-38) */
+enum { B200ISO_RANGE_INT = 0, B200ISO_RANGE_F32 = 1, B200ISO_RANGE_F64 = 2 };
+
+enum {
+  B200ISO_OK = 0,
+  B200ISO_EINVAL = -1,   /* bad argument */
+  B200ISO_ECUDA = -2,    /* CUDA runtime error (message has the CUDA string) */
+  B200ISO_ENOMEM = -3,   /* device or host allocation failed */
+  B200ISO_ESTATE = -4,   /* call order violated (e.g. generate before count) */
+  B200ISO_ECAPACITY = -5 /* caller buffer too small for the mesh */
+};
+
+/* The `method` object and the positional X, Y, Z of the reference call, flattened.
+ * iso/eps carry the VALUE; *_is_f32 carries typeof(method.iso)/typeof(method.eps)
+ * (MarchingCubes(iso=0f0) vs the default iso=0.0::Float64, src/algorithmtypes.jl:23-25,37-40).
+ * Only first(X), last(X) etc. matter (src/marching_cubes.jl:36-38). */
+typedef struct b200iso_params {
+  int32_t algo;       /* B200ISO_MC | B200ISO_MT */
+  int32_t iso_is_f32; /* 1: typeof(iso) == Float32, 0: Float64 */
+  int32_t eps_is_f32; /* MT only */
+  int32_t range_kind; /* B200ISO_RANGE_* */
+  double iso;
+  double eps;         /* MT only (default 1e-3) */
+  double x0, x1, y0, y1, z0, z1;
+} b200iso_params;
+
+/* ---- lifetime ------------------------------------------------------------------------------------ */
+/* Creates a handle bound to CUDA device `device`; it owns a stream and all device scratch. */
+int b200iso_create(b200iso_handle** out, int device);
+int b200iso_destroy(b200iso_handle* h);
+/* Thread-local message of the last failing call. */
+const char* b200iso_last_error(void);
+/* Library/ABI version (major*1000 + minor). */
+int b200iso_version(void);
+/* Run on the caller's CUDA stream (a cudaStream_t); NULL restores the handle's own stream. */
+int b200iso_set_stream(b200iso_handle* h, void* cuda_stream);
+
+/* ---- the drop-in pair: replaces the body of isosurface(sdf, method, X, Y, Z) ---------------------------
+ * b200iso_count   : classify + count + scan.  `sdf` is Float32, host or device (mem), nx*ny*nz samples with
+ *                   leading dimension ldx.  Reports the mesh size and the vertex element type
+ *                   (vert_is_f64: 0 => Float32 triples, 1 => Float64 triples) so the caller can allocate
+ *                   `Vector{NTuple{3,T}}(undef, nverts)` / `Vector{NTuple{3,Int}}(undef, nfaces)`.
+ * b200iso_generate: writes 3*nverts vertex scalars and 3*nfaces Int64 indices into caller memory
+ *                   (host or device).  `vertex_base` is added to every face index: 0 for a whole
+ *                   volume, the global index base of the slab's first vertex for an x-slab shard. */
+int b200iso_count(b200iso_handle* h, const b200iso_params* p, const float* sdf, int mem, int64_t nx, int64_t ny,
+                  int64_t nz, int64_t ldx, int64_t* nverts, int64_t* nfaces, int* vert_is_f64);
+int b200iso_generate(b200iso_handle* h, void* verts, int64_t* faces, int mem, int64_t vertex_base);
+
+/* ---- asynchronous device-resident form (no host synchronisation; for pipelines and sharding) ---------
+ * b200iso_count_async   : enqueues classify/count/scan on the handle's stream; the totals
+ *                         {nverts, nfaces} are written to totals_dev (device int64[2]) -- the buffer a
+ *                         sharded caller hands to its NCCL all-gather.
+ * b200iso_generate_async: enqueues generate into device buffers of capacity vcap vertices / fcap faces
+ *                         (elements beyond capacity are dropped; check the totals afterwards).
+ *                         The face index base is vertex_base + (vertex_base_dev ? *vertex_base_dev : 0),
+ *                         read on the device when the kernel runs.
+ * b200iso_totals        : synchronises the stream and returns the totals of the last count. */
+int b200iso_count_async(b200iso_handle* h, const b200iso_params* p, const float* sdf_dev, int64_t nx, int64_t ny,
+                        int64_t nz, int64_t ldx, int64_t* totals_dev);
+int b200iso_generate_async(b200iso_handle* h, void* verts_dev, int64_t vcap, int64_t* faces_dev, int64_t fcap,
+                           const int64_t* vertex_base_dev, int64_t vertex_base);
+int b200iso_totals(b200iso_handle* h, int64_t* nverts, int64_t* nfaces, int* vert_is_f64);
+
+/* ---- parity / introspection ----------------------------------------------------------------------------
+ * Per-voxel case index (_get_cubeindex, src/common.jl:10-20; corner order of the counted algo) for the
+ * last counted field, (nx-1)(ny-1)(nz-1) bytes in scan-rank order ((x*(ny-1)+y)*(nz-1)+z). */
+int b200iso_case_indices(b200iso_handle* h, uint8_t* out, int mem);
+/* Device milliseconds of the stages of the last count/generate pair, measured with CUDA events on the
+ * handle's stream: ms[0] classify (sign-pack), ms[1] count+scan, ms[2] generate, ms[3] host->device copy,
+ * ms[4] device->host copy.  n = number of floats the caller provides (<= 5 are written).
+ * Timing must be switched on first (it adds event records to the stream). */
+int b200iso_enable_timing(b200iso_handle* h, int on);
+int b200iso_timings(b200iso_handle* h, float* ms, int n);
+/* Number of kernels launched by this handle since creation (bench.py reports it as gpu_launches). */
+int64_t b200iso_launch_count(b200iso_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ISO_H */

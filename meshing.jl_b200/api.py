@@ -1,0 +1,188 @@
+"""Host-side mirror of the reference's public interface for the hot path.
+
+Same names, argument meaning and result layout as Meshing.jl v0.7.0:
+
+    isosurface(sdf, method, X, Y, Z) -> (vertices, faces)        src/marching_cubes.jl:27,
+                                                                 src/marching_tetrahedra.jl:129
+    isosurface(sdf, X, Y, Z) == isosurface(sdf, MarchingCubes(), X, Y, Z)   src/isosurface.jl:30-32
+    MarchingCubes(iso=0.0), MarchingTetrahedra(iso=0.0, eps=1e-3)           src/algorithmtypes.jl:23-40
+
+Julia carries the types of `iso`, `eps` and of the range endpoints in the method/range objects; here they
+are carried by the Python scalar type: `numpy.float32` <-> Float32, Python `float`/`numpy.float64` <->
+Float64, Python `int` <-> Int.  `Float32` / `Float64` are exported as aliases, so the Float32-vertex call of
+the benchmark reads `isosurface(sdf, MarchingCubes(iso=Float32(0)))`.
+
+Everything is computed by libb200iso.so (CUDA, sm_100a).  Inputs the accelerated path does not cover
+(non-Float32 fields) raise TypeError -- there is no CPU fallback.
+"""
+from dataclasses import dataclass
+from typing import Any
+
+import numpy as np
+
+from . import capi
+
+Float32 = np.float32
+Float64 = np.float64
+
+
+@dataclass(frozen=True)
+class MarchingCubes:
+    """MarchingCubes(iso=0.0)  (src/algorithmtypes.jl:23-25)"""
+    iso: Any = 0.0
+
+
+@dataclass(frozen=True)
+class MarchingTetrahedra:
+    """MarchingTetrahedra(iso=0.0, eps=1e-3)  (src/algorithmtypes.jl:37-40)"""
+    iso: Any = 0.0
+    eps: Any = 1e-3
+
+
+def _scalar_kind(v, what):
+    """-> (value as float, is_f32).  Int behaves like the other operands' type (Float32 here, because the
+    field is Float32: promote_type(Int64, Float32) == Float32), provided it is exact in Float32."""
+    if isinstance(v, (np.float32,)):
+        return float(v), True
+    if isinstance(v, (bool, np.bool_)):
+        raise TypeError(f"{what} must be a real number")
+    if isinstance(v, (int, np.integer)):
+        if float(np.float32(v)) != float(v):
+            raise TypeError(f"integer {what}={v} is not exactly representable in Float32")
+        return float(v), True
+    if isinstance(v, (float, np.float64)):
+        return float(v), False
+    raise TypeError(f"unsupported type for {what}: {type(v).__name__} (Float32, Float64 or Int)")
+
+
+def _range_kind(r, name):
+    """first/last element and element kind of a range-like (tuple, list, range, ndarray).  Only the
+    endpoints are used, like LinRange(first(X), last(X), n) in src/marching_cubes.jl:36-38."""
+    if isinstance(r, range):
+        if len(r) == 0:
+            raise ValueError(f"{name} is empty")
+        return float(r[0]), float(r[-1]), capi.RANGE_INT
+    a = r[0], r[-1]
+    kinds = set()
+    for v in a:
+        if isinstance(v, (int, np.integer)) and not isinstance(v, (bool, np.bool_)):
+            kinds.add(capi.RANGE_INT)
+        elif isinstance(v, np.float32):
+            kinds.add(capi.RANGE_F32)
+        elif isinstance(v, (float, np.float64)):
+            kinds.add(capi.RANGE_F64)
+        else:
+            raise TypeError(f"unsupported endpoint type in {name}: {type(v).__name__}")
+    return float(a[0]), float(a[1]), max(kinds)
+
+
+def make_params(method, X=(-1, 1), Y=(-1, 1), Z=(-1, 1)):
+    """Flatten (method, X, Y, Z) of the reference call into struct b200iso_params."""
+    p = capi.Params()
+    if isinstance(method, MarchingCubes):
+        p.algo = capi.MC
+        p.iso, isf = _scalar_kind(method.iso, "iso")
+        p.eps, epf = 1e-3, True
+    elif isinstance(method, MarchingTetrahedra):
+        p.algo = capi.MT
+        p.iso, isf = _scalar_kind(method.iso, "iso")
+        p.eps, epf = _scalar_kind(method.eps, "eps")
+    else:
+        raise TypeError("method must be MarchingCubes(...) or MarchingTetrahedra(...)")
+    p.iso_is_f32, p.eps_is_f32 = int(isf), int(epf)
+    x0, x1, kx = _range_kind(X, "X")
+    y0, y1, ky = _range_kind(Y, "Y")
+    z0, z1, kz = _range_kind(Z, "Z")
+    if len({kx, ky, kz}) != 1:
+        raise TypeError("X, Y, Z must have the same element type (Int, Float32 or Float64)")
+    p.range_kind = kx
+    p.x0, p.x1, p.y0, p.y1, p.z0, p.z1 = x0, x1, y0, y1, z0, z1
+    return p
+
+
+_handles = {}
+
+
+def get_handle(device=0):
+    h = _handles.get(device)
+    if h is None:
+        h = _handles[device] = capi.Handle(device)
+    return h
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def isosurface(sdf, *args, device=None):
+    """isosurface(sdf[, method][, X, Y, Z]) -> (vertices, faces)
+
+    sdf      : 3-D Float32 array, `sdf[x, y, z]`.  numpy array (host; any strides, made x-contiguous like a
+               Julia Array) or a CUDA torch tensor whose x stride is 1 (device-resident: outputs are CUDA
+               tensors too and nothing crosses PCIe).
+    method   : MarchingCubes(iso=...) (default) or MarchingTetrahedra(iso=..., eps=...)
+    X, Y, Z  : ranges whose first/last elements give the extent; default -1:1 on every axis
+    returns  : vertices (nverts, 3) Float32|Float64 by the reference's promotion rule, faces (nfaces, 3)
+               int64, 1-based, in the reference's order (x-outermost, z-innermost voxel scan).
+    """
+    if args and isinstance(args[0], (MarchingCubes, MarchingTetrahedra)):
+        method, rest = args[0], args[1:]
+    else:
+        method, rest = MarchingCubes(), args  # src/isosurface.jl:30-32
+    if len(rest) not in (0, 3):
+        raise TypeError("isosurface(sdf[, method][, X, Y, Z])")
+    params = make_params(method, *rest)
+
+    if _is_torch(sdf):
+        return _isosurface_torch(sdf, params, device)
+    a = np.asarray(sdf)
+    if a.ndim != 3:
+        raise TypeError("sdf must be a 3-D array")
+    if a.dtype != np.float32:
+        raise TypeError(f"the B200 path accepts Float32 fields only (got {a.dtype}); there is no CPU fallback")
+    a = np.asfortranarray(a)
+    nx, ny, nz = a.shape
+    h = get_handle(0 if device is None else device)
+    nv, nf, f64 = h.count(params, a.ctypes.data, capi.HOST, nx, ny, nz, nx)
+    verts = np.empty((nv, 3), dtype=np.float64 if f64 else np.float32)
+    faces = np.empty((nf, 3), dtype=np.int64)
+    h.generate(verts.ctypes.data, faces.ctypes.data, capi.HOST, 0)
+    return verts, faces
+
+
+def _isosurface_torch(t, params, device):
+    import torch
+
+    if t.dim() != 3 or t.dtype != torch.float32 or not t.is_cuda:
+        raise TypeError("torch input must be a 3-D float32 CUDA tensor")
+    nx, ny, nz = t.shape
+    sx, sy, sz = t.stride()
+    if nx > 1 and sx != 1:
+        raise TypeError("torch input must be x-contiguous (stride 1 on dim 0), i.e. Julia/Fortran order")
+    ldx = sy if ny > 1 else max(nx, 1)
+    if ny > 1 and nz > 1 and sz != ldx * ny:
+        raise TypeError("torch input must have strides (1, ldx, ldx*ny)")
+    dev = t.device.index
+    h = get_handle(dev)
+    with torch.cuda.device(dev):
+        h.set_stream(torch.cuda.current_stream().cuda_stream)
+        nv, nf, f64 = h.count(params, t.data_ptr(), capi.DEVICE, nx, ny, nz, ldx)
+        verts = torch.empty((nv, 3), dtype=torch.float64 if f64 else torch.float32, device=t.device)
+        faces = torch.empty((nf, 3), dtype=torch.int64, device=t.device)
+        h.generate(verts.data_ptr(), faces.data_ptr(), capi.DEVICE, 0)
+    return verts, faces
+
+
+def case_indices(sdf, method=None, device=0):
+    """Per-voxel case index (_get_cubeindex, src/common.jl:10-20) in scan-rank order, computed on the GPU
+    from the classify kernel's bit-field (parity check hook)."""
+    method = method or MarchingCubes()
+    a = np.asfortranarray(np.asarray(sdf))
+    if a.dtype != np.float32 or a.ndim != 3:
+        raise TypeError("3-D Float32 field expected")
+    nx, ny, nz = a.shape
+    h = get_handle(device)
+    h.count(make_params(method), a.ctypes.data, capi.HOST, nx, ny, nz, nx)
+    out = np.empty(max(nx - 1, 0) * max(ny - 1, 0) * max(nz - 1, 0), dtype=np.uint8)
+    h.case_indices(out.ctypes.data, capi.HOST)
+    return out

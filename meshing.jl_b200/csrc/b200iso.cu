@@ -1,0 +1,405 @@
+// b200iso.cu -- C ABI (include/b200iso.h) and host orchestration of the sm_100a isosurface kernels.
+// Replaces the bodies of isosurface(::MarchingCubes) (src/marching_cubes.jl:27-64) and
+// isosurface(::MarchingTetrahedra) (src/marching_tetrahedra.jl:129-163) of the reference.
+#include "../../include/b200iso.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+
+#include "iso_kernels.cuh"
+#include "mt_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return fail(e_ == cudaErrorMemoryAllocation ? B200ISO_ENOMEM : B200ISO_ECUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);                                    \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  int reserve(size_t n) {
+    if (n <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr, cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(B200ISO_ENOMEM, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
+    }
+    cap = n;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr, cap = 0;
+  }
+};
+
+// smallest float t such that for every float s: (double)s < iso  <=>  s < t   (strict compare,
+// src/common.jl:11-18, after Julia's promotion of both sides to Float64).
+float threshold_for(double iso, bool iso_is_f32) {
+  if (iso_is_f32) return (float)iso;
+  if (std::isnan(iso)) return std::numeric_limits<float>::quiet_NaN();
+  float f = (float)iso;  // round to nearest
+  if ((double)f < iso) f = std::nextafterf(f, std::numeric_limits<float>::infinity());
+  return f;
+}
+
+}  // namespace
+
+struct b200iso_handle {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  DevBuf<uint32_t> bits;
+  DevBuf<unsigned long long> status;
+  DevBuf<double> coords;
+  DevBuf<float> field;           // staging of a host field
+  DevBuf<unsigned char> vstage;  // staging of vertices for host output
+  DevBuf<long long> fstage;
+  unsigned int* ticket = nullptr;
+  long long* totals_dev = nullptr;   // device int64[2]
+  long long* totals_host = nullptr;  // pinned int64[2]
+  // last counted problem
+  bool counted = false, totals_known = false;
+  b200iso_params prm{};
+  iso::Grid grid{};
+  const float* sdf_dev = nullptr;
+  long long nblocks = 0;
+  int vert_is_f64 = 0;
+  long long nverts = 0, nfaces = 0;
+  // timing
+  bool timing = false;
+  cudaEvent_t ev[8] = {};
+  float ms[5] = {0, 0, 0, 0, 0};
+  int64_t launches = 0;
+};
+
+namespace {
+
+int vertex_is_f64(const b200iso_params& p) {
+  // float(promote_type(eltype(X), eltype(Y), eltype(Z), Float32, typeof(iso)[, typeof(eps)]))
+  return (!p.iso_is_f32) || p.range_kind == B200ISO_RANGE_F64 || (p.algo == B200ISO_MT && !p.eps_is_f32);
+}
+
+int check_params(const b200iso_params* p, int64_t nx, int64_t ny, int64_t nz, int64_t ldx) {
+  if (!p) return fail(B200ISO_EINVAL, "params is NULL");
+  if (p->algo != B200ISO_MC && p->algo != B200ISO_MT) return fail(B200ISO_EINVAL, "unknown algo %d", p->algo);
+  if (p->range_kind < 0 || p->range_kind > 2) return fail(B200ISO_EINVAL, "unknown range_kind %d", p->range_kind);
+  if (nx < 0 || ny < 0 || nz < 0) return fail(B200ISO_EINVAL, "negative dimension");
+  if (ldx < nx) return fail(B200ISO_EINVAL, "ldx (%lld) < nx (%lld)", (long long)ldx, (long long)nx);
+  if (nx > 65536 || ny > 65536 || nz > 65536) return fail(B200ISO_EINVAL, "dimension larger than 65536 is not supported");
+  return 0;
+}
+
+int enqueue_count(b200iso_handle* h, const b200iso_params* p, const float* sdf_dev, int64_t nx, int64_t ny, int64_t nz,
+                  int64_t ldx, long long* totals_out) {
+  cudaStream_t st = h->stream;
+  h->prm = *p;
+  h->sdf_dev = sdf_dev;
+  h->vert_is_f64 = vertex_is_f64(*p);
+  h->counted = false, h->totals_known = false;
+  iso::Grid& g = h->grid;
+  g.nx = (int)nx, g.ny = (int)ny, g.nz = (int)nz;
+  g.ldx = ldx, g.plane = (long long)ldx * ny;
+  const int words = (int)((nz + 31) / 32);
+  g.W = (words + 3) / 4 * 4;
+  if (g.W == 0) g.W = 4;
+  g.Wq = g.W / 4;
+  g.row_words = (long long)ny * g.W;
+  g.quads_per_row = (int)((ny > 0 ? ny - 1 : 0) * g.Wq);
+  g.blocks_per_row = (g.quads_per_row + iso::CB_THREADS - 1) / iso::CB_THREADS;
+  h->nblocks = (nx > 1 && ny > 1 && nz > 1) ? (long long)(nx - 1) * g.blocks_per_row : 0;
+
+  if (h->nblocks == 0) {  // a dimension < 2: zero voxels, empty mesh (src/marching_cubes.jl:40)
+    CU(cudaMemsetAsync(h->totals_dev, 0, 2 * sizeof(long long), st));
+    if (totals_out) CU(cudaMemsetAsync(totals_out, 0, 2 * sizeof(long long), st));
+    h->counted = true;
+    return 0;
+  }
+  const size_t nbits = (size_t)nx * ny * g.W;
+  if (int rc = h->bits.reserve(nbits)) return rc;
+  if (int rc = h->status.reserve((size_t)h->nblocks * 2)) return rc;
+  if (int rc = h->coords.reserve((size_t)(nx + ny + nz))) return rc;
+
+  if (h->timing) CU(cudaEventRecord(h->ev[0], st));
+  // (1) sign-pack
+  {
+    const bool vec = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(sdf_dev) & 15) == 0);
+    const int nxseg = (int)((nx + iso::SP_XSEG - 1) / iso::SP_XSEG);
+    const int nzc = (g.W + iso::SP_ZW - 1) / iso::SP_ZW;
+    const long long ntasks = (long long)nxseg * ny * nzc;
+    const unsigned nb = (unsigned)((ntasks + iso::SP_WARPS - 1) / iso::SP_WARPS);
+    const float thr = threshold_for(p->iso, p->iso_is_f32 != 0);
+    if (vec)
+      iso::signpack_kernel<true><<<nb, iso::SP_WARPS * 32, 0, st>>>(sdf_dev, h->bits.p, g.nx, g.ny, g.nz, g.ldx, g.W, thr, nxseg, ntasks);
+    else
+      iso::signpack_kernel<false><<<nb, iso::SP_WARPS * 32, 0, st>>>(sdf_dev, h->bits.p, g.nx, g.ny, g.nz, g.ldx, g.W, thr, nxseg, ntasks);
+    CU(cudaGetLastError());
+    h->launches++;
+  }
+  if (h->timing) CU(cudaEventRecord(h->ev[1], st));
+  // (2) count + decoupled look-back scan
+  CU(cudaMemsetAsync(h->status.p, 0, (size_t)h->nblocks * 2 * sizeof(unsigned long long), st));
+  CU(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int), st));
+  if (p->algo == B200ISO_MC)
+    iso::count_kernel<0><<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->status.p, h->ticket, h->nblocks, h->totals_dev, totals_out);
+  else
+    iso::count_kernel<1><<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->status.p, h->ticket, h->nblocks, h->totals_dev, totals_out);
+  CU(cudaGetLastError());
+  h->launches++;
+  // grid coordinates (LinRange), consumed by generate
+  {
+    const int n = (int)(nx + ny + nz);
+    iso::coords_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->coords.p, g.nx, g.ny, g.nz, p->x0, p->x1, p->y0, p->y1, p->z0, p->z1,
+                                                        p->range_kind == B200ISO_RANGE_F32);
+    CU(cudaGetLastError());
+    h->launches++;
+  }
+  if (h->timing) CU(cudaEventRecord(h->ev[2], st));
+  h->counted = true;
+  return 0;
+}
+
+int enqueue_generate(b200iso_handle* h, void* verts_dev, int64_t vcap, int64_t* faces_dev, int64_t fcap,
+                     const int64_t* vertex_base_dev, int64_t vertex_base) {
+  if (!h->counted) return fail(B200ISO_ESTATE, "generate called before count");
+  cudaStream_t st = h->stream;
+  if (h->timing) CU(cudaEventRecord(h->ev[3], st));
+  if (h->nblocks > 0) {
+    const b200iso_params& p = h->prm;
+    iso::GenArgs a{};
+    a.sdf = h->sdf_dev, a.bits = h->bits.p, a.status = h->status.p, a.coords = h->coords.p;
+    a.verts = verts_dev, a.faces = (long long*)faces_dev, a.vcap = vcap, a.fcap = fcap;
+    a.vbase_dev = (const long long*)vertex_base_dev, a.vbase = vertex_base;
+    a.iso_d = p.iso, a.iso_f = (float)p.iso, a.eps_d = p.eps, a.eps_f = (float)p.eps;
+    const unsigned nb = (unsigned)h->nblocks;
+    const bool pf32 = p.range_kind == B200ISO_RANGE_F32;
+    if (p.algo == B200ISO_MC) {
+      if (!p.iso_is_f32) iso::mc_generate_kernel<2, double><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+      else if (pf32) iso::mc_generate_kernel<1, float><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+      else if (h->vert_is_f64) iso::mc_generate_kernel<0, double><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+      else iso::mc_generate_kernel<0, float><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+    } else {
+      if (int rc = iso::launch_mt_generate(a, h->grid, p, h->vert_is_f64, nb, st)) return fail(B200ISO_EINVAL, "MT launch failed (%d)", rc);
+    }
+    CU(cudaGetLastError());
+    h->launches++;
+  }
+  if (h->timing) CU(cudaEventRecord(h->ev[4], st));
+  return 0;
+}
+
+int fetch_totals(b200iso_handle* h) {
+  if (!h->counted) return fail(B200ISO_ESTATE, "no counted field");
+  if (!h->totals_known) {
+    CU(cudaMemcpyAsync(h->totals_host, h->totals_dev, 2 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->nverts = h->totals_host[0], h->nfaces = h->totals_host[1];
+    h->totals_known = true;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200iso_version(void) { return 1000; }
+const char* b200iso_last_error(void) { return g_err; }
+
+int b200iso_create(b200iso_handle** out, int device) {
+  if (!out) return fail(B200ISO_EINVAL, "out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(B200ISO_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  CU(cudaSetDevice(device));
+  b200iso_handle* h = new b200iso_handle();
+  h->device = device;
+  CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  CU(cudaMalloc((void**)&h->ticket, sizeof(unsigned int)));
+  CU(cudaMalloc((void**)&h->totals_dev, 2 * sizeof(long long)));
+  CU(cudaMallocHost((void**)&h->totals_host, 2 * sizeof(long long)));
+  for (auto& e : h->ev) CU(cudaEventCreate(&e));
+  *out = h;
+  return 0;
+}
+
+int b200iso_destroy(b200iso_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->bits.release(), h->status.release(), h->coords.release(), h->field.release(), h->vstage.release(), h->fstage.release();
+  if (h->ticket) cudaFree(h->ticket);
+  if (h->totals_dev) cudaFree(h->totals_dev);
+  if (h->totals_host) cudaFreeHost(h->totals_host);
+  for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return 0;
+}
+
+int b200iso_set_stream(b200iso_handle* h, void* cuda_stream) {
+  if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return 0;
+}
+
+int b200iso_count_async(b200iso_handle* h, const b200iso_params* p, const float* sdf_dev, int64_t nx, int64_t ny,
+                        int64_t nz, int64_t ldx, int64_t* totals_dev) {
+  if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  if (int rc = check_params(p, nx, ny, nz, ldx)) return rc;
+  if (!sdf_dev && nx * ny * nz > 0) return fail(B200ISO_EINVAL, "sdf is NULL");
+  CU(cudaSetDevice(h->device));
+  return enqueue_count(h, p, sdf_dev, nx, ny, nz, ldx, (long long*)totals_dev);
+}
+
+int b200iso_generate_async(b200iso_handle* h, void* verts_dev, int64_t vcap, int64_t* faces_dev, int64_t fcap,
+                           const int64_t* vertex_base_dev, int64_t vertex_base) {
+  if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  if (vcap < 0 || fcap < 0) return fail(B200ISO_EINVAL, "negative capacity");
+  if ((vcap > 0 && !verts_dev) || (fcap > 0 && !faces_dev)) return fail(B200ISO_EINVAL, "output pointer is NULL");
+  CU(cudaSetDevice(h->device));
+  return enqueue_generate(h, verts_dev, vcap, faces_dev, fcap, vertex_base_dev, vertex_base);
+}
+
+int b200iso_totals(b200iso_handle* h, int64_t* nverts, int64_t* nfaces, int* vert_is_f64) {
+  if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  CU(cudaSetDevice(h->device));
+  if (int rc = fetch_totals(h)) return rc;
+  if (nverts) *nverts = h->nverts;
+  if (nfaces) *nfaces = h->nfaces;
+  if (vert_is_f64) *vert_is_f64 = h->vert_is_f64;
+  return 0;
+}
+
+int b200iso_count(b200iso_handle* h, const b200iso_params* p, const float* sdf, int mem, int64_t nx, int64_t ny, int64_t nz,
+                  int64_t ldx, int64_t* nverts, int64_t* nfaces, int* vert_is_f64) {
+  if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  if (int rc = check_params(p, nx, ny, nz, ldx)) return rc;
+  if (mem != B200ISO_HOST && mem != B200ISO_DEVICE) return fail(B200ISO_EINVAL, "bad mem kind %d", mem);
+  if (!sdf && nx * ny * nz > 0) return fail(B200ISO_EINVAL, "sdf is NULL");
+  CU(cudaSetDevice(h->device));
+  const float* dev = sdf;
+  int64_t dldx = ldx;
+  h->ms[3] = 0;
+  if (mem == B200ISO_HOST && nx * ny * nz > 0) {
+    // stage with a 16-byte aligned leading dimension so the 128-bit load path always applies
+    dldx = (nx + 3) / 4 * 4;
+    if (int rc = h->field.reserve((size_t)dldx * ny * nz)) return rc;
+    if (h->timing) CU(cudaEventRecord(h->ev[5], h->stream));
+    if (dldx == ldx)
+      CU(cudaMemcpyAsync(h->field.p, sdf, (size_t)ldx * ny * nz * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    else
+      CU(cudaMemcpy2DAsync(h->field.p, (size_t)dldx * sizeof(float), sdf, (size_t)ldx * sizeof(float), (size_t)nx * sizeof(float),
+                           (size_t)ny * nz, cudaMemcpyHostToDevice, h->stream));
+    if (h->timing) CU(cudaEventRecord(h->ev[6], h->stream));
+    dev = h->field.p;
+  }
+  if (int rc = enqueue_count(h, p, dev, nx, ny, nz, dldx, nullptr)) return rc;
+  if (int rc = fetch_totals(h)) return rc;
+  if (h->timing) {
+    if (h->nblocks > 0) {
+      cudaEventElapsedTime(&h->ms[0], h->ev[0], h->ev[1]);
+      cudaEventElapsedTime(&h->ms[1], h->ev[1], h->ev[2]);
+      if (mem == B200ISO_HOST) cudaEventElapsedTime(&h->ms[3], h->ev[5], h->ev[6]);
+    } else {
+      h->ms[0] = h->ms[1] = 0;
+    }
+  }
+  if (nverts) *nverts = h->nverts;
+  if (nfaces) *nfaces = h->nfaces;
+  if (vert_is_f64) *vert_is_f64 = h->vert_is_f64;
+  return 0;
+}
+
+int b200iso_generate(b200iso_handle* h, void* verts, int64_t* faces, int mem, int64_t vertex_base) {
+  if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  if (mem != B200ISO_HOST && mem != B200ISO_DEVICE) return fail(B200ISO_EINVAL, "bad mem kind %d", mem);
+  CU(cudaSetDevice(h->device));
+  if (int rc = fetch_totals(h)) return rc;
+  const size_t vsz = h->vert_is_f64 ? 8 : 4;
+  if ((h->nverts > 0 && !verts) || (h->nfaces > 0 && !faces)) return fail(B200ISO_EINVAL, "output pointer is NULL");
+  h->ms[4] = 0;
+  if (mem == B200ISO_DEVICE) {
+    if (int rc = enqueue_generate(h, verts, h->nverts, faces, h->nfaces, nullptr, vertex_base)) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+  } else {
+    if (int rc = h->vstage.reserve((size_t)h->nverts * 3 * vsz + 16)) return rc;
+    if (int rc = h->fstage.reserve((size_t)h->nfaces * 3 + 2)) return rc;
+    if (int rc = enqueue_generate(h, h->vstage.p, h->nverts, (int64_t*)h->fstage.p, h->nfaces, nullptr, vertex_base)) return rc;
+    if (h->timing) CU(cudaEventRecord(h->ev[5], h->stream));
+    if (h->nverts) CU(cudaMemcpyAsync(verts, h->vstage.p, (size_t)h->nverts * 3 * vsz, cudaMemcpyDeviceToHost, h->stream));
+    if (h->nfaces) CU(cudaMemcpyAsync(faces, h->fstage.p, (size_t)h->nfaces * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (h->timing) CU(cudaEventRecord(h->ev[6], h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->timing) cudaEventElapsedTime(&h->ms[4], h->ev[5], h->ev[6]);
+  }
+  if (h->timing) cudaEventElapsedTime(&h->ms[2], h->ev[3], h->ev[4]);
+  return 0;
+}
+
+int b200iso_case_indices(b200iso_handle* h, uint8_t* out, int mem) {
+  if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  if (!h->counted) return fail(B200ISO_ESTATE, "no counted field");
+  CU(cudaSetDevice(h->device));
+  const iso::Grid& g = h->grid;
+  if (h->nblocks == 0) return 0;
+  const long long nvox = (long long)(g.nx - 1) * (g.ny - 1) * (g.nz - 1);
+  if (!out) return fail(B200ISO_EINVAL, "out is NULL");
+  uint8_t* dev = out;
+  DevBuf<uint8_t> tmp;
+  if (mem == B200ISO_HOST) {
+    if (int rc = tmp.reserve((size_t)nvox)) return rc;
+    dev = tmp.p;
+  }
+  const unsigned nb = (unsigned)((nvox + 255) / 256);
+  if (h->prm.algo == B200ISO_MC) iso::case_kernel<0><<<nb, 256, 0, h->stream>>>(h->bits.p, g, dev, nvox);
+  else iso::case_kernel<1><<<nb, 256, 0, h->stream>>>(h->bits.p, g, dev, nvox);
+  cudaError_t e = cudaGetLastError();
+  h->launches++;
+  if (e == cudaSuccess && mem == B200ISO_HOST) e = cudaMemcpyAsync(out, dev, (size_t)nvox, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  tmp.release();
+  if (e != cudaSuccess) return fail(B200ISO_ECUDA, "case_indices: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int b200iso_enable_timing(b200iso_handle* h, int on) {
+  if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  h->timing = on != 0;
+  return 0;
+}
+
+int b200iso_timings(b200iso_handle* h, float* ms, int n) {
+  if (!h || !ms) return fail(B200ISO_EINVAL, "NULL argument");
+  for (int i = 0; i < n && i < 5; ++i) ms[i] = h->ms[i];
+  return 0;
+}
+
+int64_t b200iso_launch_count(b200iso_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

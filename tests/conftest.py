@@ -1,0 +1,27 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    """The CPU oracle harness (builds liboracle.so on first use)."""
+    from oracle import harness
+    harness.build()
+    return harness
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    """The product package `meshing.jl_b200` (loaded by path: the directory name has a dot)."""
+    from __graft_entry__ import load_package
+    return load_package()

@@ -1,0 +1,62 @@
+"""CPU-side checks of the product's boundary: the library loads, exports every declared symbol, and the
+host mirror maps the reference's call forms onto struct b200iso_params (no compute without a GPU)."""
+import numpy as np
+import pytest
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    L = pkg.capi.load()
+    names = pkg.capi.declared_symbols()
+    assert "b200iso_count" in names and "b200iso_generate" in names and len(names) >= 14
+    for n in names:
+        assert hasattr(L, n), n
+    assert L.b200iso_version() >= 1000
+
+
+def test_params_mirror_reference_call_forms(pkg):
+    api, capi = pkg.api, pkg.capi
+    p = api.make_params(api.MarchingCubes())  # MarchingCubes() => iso = 0.0::Float64, X = Y = Z = -1:1
+    assert (p.algo, p.iso, p.iso_is_f32, p.range_kind) == (capi.MC, 0.0, 0, capi.RANGE_INT)
+    assert (p.x0, p.x1, p.y0, p.y1, p.z0, p.z1) == (-1, 1, -1, 1, -1, 1)
+    p = api.make_params(api.MarchingTetrahedra(iso=api.Float32(0.5), eps=api.Float32(1e-3)), (0, 1), (0, 1), (0, 1))
+    assert (p.algo, p.iso_is_f32, p.eps_is_f32) == (capi.MT, 1, 1) and p.iso == 0.5 and p.eps == float(np.float32(1e-3))
+    p = api.make_params(api.MarchingTetrahedra(iso=100), range(-2, 3), range(0, 2), range(5, 9))  # Int iso (examples/nrrd.jl:14)
+    assert p.iso == 100.0 and p.iso_is_f32 == 1 and p.eps_is_f32 == 0 and (p.x0, p.x1, p.z0, p.z1) == (-2, 2, 5, 8)
+    rng = np.arange(-2, 2.001, 0.01)
+    p = api.make_params(api.MarchingCubes(iso=0.85), rng, rng, rng)
+    assert p.range_kind == capi.RANGE_F64 and p.x0 == -2.0 and abs(p.x1 - 2.0) < 1e-9
+    f = np.float32
+    p = api.make_params(api.MarchingCubes(iso=f(0)), (f(-2), f(2)), (f(-2), f(2)), (f(-2), f(2)))
+    assert p.range_kind == capi.RANGE_F32 and p.iso_is_f32 == 1
+
+
+def test_argument_errors(pkg):
+    api = pkg.api
+    with pytest.raises(TypeError):
+        api.make_params("MarchingCubes")
+    with pytest.raises(TypeError):
+        api.make_params(api.MarchingCubes(iso="0"))
+    with pytest.raises(TypeError):
+        api.make_params(api.MarchingCubes(), (0, 1), (0.0, 1.0), (0, 1))
+    with pytest.raises(TypeError):  # non-Float32 field: outside the accelerated path, no CPU fallback
+        api.isosurface(np.zeros((4, 4, 4), np.float64))
+    with pytest.raises(TypeError):
+        api.isosurface(np.zeros((4, 4), np.float32))
+
+
+def test_no_gpu_fails_loudly(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.capi.B200IsoError):
+        pkg.capi.Handle(0)
+
+
+def test_product_never_imports_the_oracle():
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dp, _, files in os.walk(os.path.join(root, "meshing.jl_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl", "Makefile")):
+                src = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle" not in src.lower(), os.path.join(dp, f)

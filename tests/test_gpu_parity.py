@@ -1,0 +1,226 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+Bar (BASELINE.json north_star): faces, vertex count/order and per-voxel case indices bit-exact; Float32
+vertex coordinates within 1 ulp -- these tests demand bit-exact coordinates as well (tolerance 0 ulp)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ALGOS = {"MC": 0, "MT": 1}
+
+
+def _method(pkg, algo, iso, f32, eps=1e-3):
+    conv = pkg.Float32 if f32 else float
+    if algo == "MC":
+        return pkg.MarchingCubes(iso=conv(iso))
+    return pkg.MarchingTetrahedra(iso=conv(iso), eps=conv(eps))
+
+
+def _bits_equal(a, b):
+    """Bit-exact equality of float arrays, NaNs compared by NaN-ness."""
+    if a.dtype != b.dtype or a.shape != b.shape:
+        return False
+    na, nb = np.isnan(a), np.isnan(b)
+    if not np.array_equal(na, nb):
+        return False
+    u = np.uint32 if a.dtype == np.float32 else np.uint64
+    return np.array_equal(a.view(u)[~na], b.view(u)[~nb])
+
+
+def _check(pkg, oracle, s, algo, iso=0.0, f32=True, ranges=None, rk=None, eps=1e-3):
+    rk = oracle.RANGE_INT if rk is None else rk
+    conv = {oracle.RANGE_INT: int, oracle.RANGE_F32: np.float32, oracle.RANGE_F64: float}[rk]
+    rr = ranges or ((-1, 1),) * 3
+    args = [tuple(conv(e) for e in r) for r in rr]
+    v, f = pkg.isosurface(s, _method(pkg, algo, iso, f32, eps), *args)
+    vo, fo = oracle.isosurface(s, ALGOS[algo], iso=iso, iso_is_f32=f32, eps=eps, eps_is_f32=f32, ranges=rr, range_kind=rk)
+    assert v.shape == vo.shape and f.shape == fo.shape, (v.shape, vo.shape, f.shape, fo.shape)
+    assert v.dtype == vo.dtype
+    assert np.array_equal(f, fo), "faces differ"
+    assert _bits_equal(v, vo), "vertex coordinates differ (0 ulp demanded)"
+    return v, f
+
+
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+@pytest.mark.parametrize("shape", [(16, 16, 16), (33, 20, 47), (64, 64, 64), (5, 130, 37), (129, 7, 70), (12, 9, 260)])
+def test_parity_shapes(pkg, oracle, algo, shape):
+    _check(pkg, oracle, pkg.synth.gyroid(shape), algo)
+    _check(pkg, oracle, pkg.synth.sphere(shape), algo)
+
+
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+def test_parity_dense_noise(pkg, oracle, algo):
+    """Worst case: nearly every voxel active, every one of the 254 cases occurs, multi-round blocks."""
+    s = pkg.synth.noise((40, 37, 150), seed=3)
+    _check(pkg, oracle, s, algo)
+    c = pkg.api.case_indices(s, _method(pkg, algo, 0.0, True))
+    assert np.array_equal(c, oracle.case_indices(s, ALGOS[algo], iso_is_f32=True))
+    assert len(np.unique(c)) == 256
+
+
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+@pytest.mark.parametrize("f32,rk", [(True, 0), (True, 1), (True, 2), (False, 0), (False, 1), (False, 2)])
+def test_parity_type_combinations(pkg, oracle, algo, f32, rk):
+    """typeof(iso) x eltype(X): the arithmetic modes of vertex_interp / vertPos."""
+    s = pkg.synth.gyroid((30, 41, 36))
+    _check(pkg, oracle, s, algo, iso=0.1, f32=f32, rk=rk, ranges=((-2, 3), (0, 1), (-7, -1)))
+    s2 = pkg.synth.noise((20, 21, 40), seed=11)
+    _check(pkg, oracle, s2, algo, iso=-0.3, f32=f32, rk=rk, ranges=((-2, 3), (0, 1), (-7, -1)))
+
+
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+def test_case_indices_bit_exact(pkg, oracle, algo):
+    s = pkg.synth.gyroid((70, 50, 90))
+    for iso, f32 in ((0.0, True), (0.25, False), (1e-9, False)):
+        c = pkg.api.case_indices(s, _method(pkg, algo, iso, f32))
+        assert np.array_equal(c, oracle.case_indices(s, ALGOS[algo], iso=iso, iso_is_f32=f32))
+
+
+def test_float64_iso_threshold_edge(pkg, oracle):
+    """Float32 sample vs Float64 iso compares exactly (strict <): samples equal to / adjacent to iso."""
+    base = np.float32(0.1)
+    s = np.full((6, 6, 6), base, np.float32)
+    s[::2, 1::2, ::3] = np.nextafter(base, np.float32(1))
+    s[1::2, ::2, 1::3] = np.nextafter(base, np.float32(-1))
+    for iso in (float(base), 0.1, float(np.nextafter(base, np.float32(1))), float(base) + 1e-12):
+        for algo in ("MC", "MT"):
+            c = pkg.api.case_indices(s, _method(pkg, algo, iso, False))
+            assert np.array_equal(c, oracle.case_indices(s, ALGOS[algo], iso=iso, iso_is_f32=False)), iso
+
+
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+def test_degenerate_and_tiny(pkg, oracle, algo):
+    for shape in [(1, 5, 5), (5, 1, 5), (5, 5, 1), (1, 1, 1), (2, 2, 2), (2, 3, 2), (3, 2, 33)]:
+        s = pkg.synth.noise(shape, seed=5)
+        _check(pkg, oracle, s, algo)
+    s = np.full((4, 4, 4), -1.0, np.float32)  # no surface
+    v, f = _check(pkg, oracle, s, algo)
+    assert len(v) == 0 and len(f) == 0
+
+
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+def test_nan_and_inf_samples(pkg, oracle, algo):
+    s = pkg.synth.gyroid((12, 12, 12)).copy(order="F")
+    s[3, 4, 5] = np.nan
+    s[7, 7, 7] = np.inf
+    s[2, 9, 4] = -np.inf
+    _check(pkg, oracle, s, algo)
+    c = pkg.api.case_indices(s, _method(pkg, algo, 0.0, True))
+    assert np.array_equal(c, oracle.case_indices(s, ALGOS[algo], iso_is_f32=True))
+
+
+def test_reference_kat_through_gpu(pkg):
+    """test/runtests.jl:15-33 through the CUDA path: cube index of a single voxel, and vertex_interp on a
+    2x2x2 field whose only sign change reproduces (0, .5, 0)-style interpolation."""
+    def voxel(vals):  # MC corner order -> field[x, y, z]
+        s = np.empty((2, 2, 2), np.float32)
+        for k, (x, y, z) in enumerate([(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]):
+            s[x, y, z] = vals[k]
+        return s
+    f = np.float32
+    assert pkg.api.case_indices(voxel([.1, .2, .3, .4, .5, .6, .7, .8]), pkg.MarchingCubes(iso=0.35))[0] == 0x07
+    assert pkg.api.case_indices(voxel([.5, .6, .7, .8, .9, 1., 1.1, 1.2]), pkg.MarchingCubes(iso=0.75))[0] == 0x07
+    assert pkg.api.case_indices(voxel([.9, .8, .7, .6, .5, .4, .3, .2]), pkg.MarchingCubes(iso=0.5))[0] == 0xE0
+    # one corner inside: vertices on edges 1, 9, 4 at mu = 0.5 of a [0,1]^3 voxel
+    s = voxel([-1, 1, 1, 1, 1, 1, 1, 1])
+    v, fc = pkg.isosurface(s, pkg.MarchingCubes(iso=f(0)), (0, 1), (0, 1), (0, 1))
+    assert fc.tolist() == [[3, 2, 1]]
+    assert v.tolist() == [[0.5, 0, 0], [0, 0, 0.5], [0, 0.5, 0]]
+
+
+def test_defaults_forwarder(pkg):
+    """isosurface(A) == isosurface(A, MarchingCubes())  (test/runtests.jl:76-79)"""
+    s = pkg.synth.noise((10, 10, 10), seed=1)
+    v1, f1 = pkg.isosurface(s)
+    v2, f2 = pkg.isosurface(s, pkg.MarchingCubes())
+    assert v1.dtype == np.float64 and np.array_equal(v1, v2) and np.array_equal(f1, f2)
+
+
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+def test_respect_origin_float32_field(pkg, oracle, algo):
+    """test/runtests.jl:127-149 on a Float32 copy of norm_sdf (the GPU path is Float32-field only)."""
+    g = np.arange(-100, 101) / 100.0
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    s = np.asfortranarray(np.sqrt(X * X + Y * Y + Z * Z).astype(np.float32))
+    v, f = _check(pkg, oracle, s, algo, iso=0.5, f32=False)
+    assert np.allclose(v.mean(0), 0, atol=0.015)
+    assert np.allclose(v.max(0), 0.5, atol=1e-3) and np.allclose(v.min(0), -0.5, atol=1e-3)
+
+
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+def test_noisy_spheres_float32(pkg, oracle, algo):
+    """Input of test/runtests.jl:152-172 rounded to Float32 (its Float64 form pins the oracle in
+    tests/test_oracle.py); MT result must be a closed manifold: V - F/2 == 2."""
+    import os
+    field = np.load(os.path.join(os.path.dirname(__file__), "golden", "noisy_spheres_input.npy"))
+    s = np.asfortranarray(field.astype(np.float32))
+    v, f = _check(pkg, oracle, s, algo, iso=8.0, f32=False)
+    if algo == "MT":
+        assert len(v) - len(f) // 2 == 2
+
+
+def test_device_resident_torch_path(pkg, oracle):
+    import torch
+    s = pkg.synth.gyroid((65, 40, 50))
+    for ldx in (65, 68):  # unaligned rows -> scalar-load classify; padded rows -> 128-bit loads
+        store = torch.zeros((50, 40, ldx), dtype=torch.float32, device="cuda")
+        store[:, :, :65] = torch.from_numpy(np.ascontiguousarray(s.transpose(2, 1, 0))).cuda()
+        t = store.permute(2, 1, 0)[:65]
+        for algo in ("MC", "MT"):
+            v, f = pkg.isosurface(t, _method(pkg, algo, 0.0, True))
+            vo, fo = oracle.isosurface(s, ALGOS[algo], iso_is_f32=True, eps_is_f32=True)
+            assert np.array_equal(f.cpu().numpy(), fo) and _bits_equal(v.cpu().numpy(), vo)
+
+
+def test_gyroid_synth_device_equals_host(pkg):
+    import torch
+    shape = (40, 33, 37)
+    h = pkg.synth.gyroid(shape)
+    d = pkg.synth.gyroid_torch(shape, "cuda", ldx=40)
+    assert np.array_equal(d.cpu().numpy(), h)
+    m = pkg.synth.multisphere_torus(shape)
+    md = pkg.synth.multisphere_torus(shape, xp=torch, device="cuda")
+    assert np.array_equal(md.cpu().numpy(), m)
+
+
+def test_async_capacity_and_vertex_base(pkg, oracle):
+    """Async device form: totals on the device, capacity guard, face index base (sharding hook)."""
+    import torch
+    s = pkg.synth.gyroid((48, 40, 56))
+    vo, fo = oracle.isosurface(s, 0, iso_is_f32=True)
+    t = torch.from_numpy(np.ascontiguousarray(s.transpose(2, 1, 0))).cuda().permute(2, 1, 0)
+    h = pkg.capi.Handle(0)
+    p = pkg.api.make_params(pkg.MarchingCubes(iso=pkg.Float32(0)))
+    totals = torch.zeros(2, dtype=torch.int64, device="cuda")
+    base = torch.tensor([1000], dtype=torch.int64, device="cuda")
+    h.set_stream(torch.cuda.current_stream().cuda_stream)
+    h.count_async(p, t.data_ptr(), 48, 40, 56, 48, totals.data_ptr())
+    verts = torch.full((len(vo) + 7, 3), -7.0, dtype=torch.float32, device="cuda")
+    faces = torch.full((len(fo) - 5, 3), -7, dtype=torch.int64, device="cuda")  # too small on purpose
+    h.generate_async(verts.data_ptr(), verts.shape[0], faces.data_ptr(), faces.shape[0], base.data_ptr(), 234)
+    torch.cuda.synchronize()
+    assert totals.tolist() == [len(vo), len(fo)]
+    assert h.totals()[:2] == (len(vo), len(fo))
+    assert _bits_equal(verts[: len(vo)].cpu().numpy(), vo) and (verts[len(vo):] == -7).all()
+    assert np.array_equal(faces.cpu().numpy(), fo[: len(fo) - 5] + 1234)
+    h.close()
+
+
+@pytest.mark.parametrize("algo,n", [("MC", 256), ("MT", 192)])
+def test_parity_medium_gyroid(pkg, oracle, algo, n):
+    _check(pkg, oracle, pkg.synth.gyroid(n), algo)
+
+
+def test_parity_config1_sphere128(pkg, oracle):
+    """BASELINE.json configs[0]: MC on the 128^3 sphere SDF."""
+    v, f = _check(pkg, oracle, pkg.synth.sphere(128), "MC")
+    assert v.shape == (76032, 3) and f.shape == (38012, 3)
+
+
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+def test_parity_config_512_gyroid(pkg, oracle, algo):
+    """BASELINE.json configs[1], configs[2]: 512^3 gyroid, full oracle comparison."""
+    s = pkg.synth.gyroid(512)
+    v, f = _check(pkg, oracle, s, algo)
+    if algo == "MC":
+        assert abs(len(v) - 10123197) < 2000 and abs(len(f) - 5061727) < 1000  # SURVEY.md Appendix C estimates

@@ -1,0 +1,27 @@
+#!/usr/bin/env python3
+"""Quick per-stage device timing of the pipeline on device-resident gyroids (development aid)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from __graft_entry__ import load_package
+pkg = load_package()
+algo = sys.argv[1] if len(sys.argv) > 1 else "MC"
+sizes = [int(a) for a in sys.argv[2:]] or [256, 512, 1024]
+h = pkg.capi.Handle(0)
+h.enable_timing(True)
+for n in sizes:
+    t = pkg.synth.gyroid_torch(n, "cuda")
+    torch.cuda.synchronize()
+    m = pkg.MarchingCubes(iso=pkg.Float32(0)) if algo == "MC" else pkg.MarchingTetrahedra(iso=pkg.Float32(0), eps=pkg.Float32(1e-3))
+    p = pkg.api.make_params(m)
+    for it in range(4):
+        nv, nf, f64 = h.count(p, t.data_ptr(), pkg.capi.DEVICE, n, n, n, t.stride(1))
+        verts = torch.empty((nv, 3), dtype=torch.float32, device="cuda")
+        faces = torch.empty((nf, 3), dtype=torch.int64, device="cuda")
+        h.generate(verts.data_ptr(), faces.data_ptr(), pkg.capi.DEVICE, 0)
+        tm = h.timings()
+    tot = tm["classify_ms"] + tm["count_scan_ms"] + tm["generate_ms"]
+    B = 4 * n ** 3 + 12 * nv + 24 * nf
+    print(f"{algo} n={n} nv={nv} nf={nf} classify={tm['classify_ms']:.3f} count={tm['count_scan_ms']:.3f} gen={tm['generate_ms']:.3f} "
+          f"total={tot:.3f} ms  {(n-1)**3/tot/1e6:.1f} Gvox/s  {B/tot/1e6:.0f} GB/s  classify {4*n**3/tm['classify_ms']/1e6:.0f} GB/s", flush=True)
+    del t, verts, faces
