@@ -13,6 +13,7 @@
 
 #include "iso_kernels.cuh"
 #include "mt_kernels.cuh"
+#include "count_kernel.cuh"
 
 namespace {
 
@@ -72,6 +73,7 @@ struct b200iso_handle {
   int device = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   DevBuf<uint32_t> bits;
+  DevBuf<uint32_t> celloff;      // MT: per-cell vertex prefix inside its block
   DevBuf<unsigned long long> status;
   DevBuf<double> coords;
   DevBuf<float> field;           // staging of a host field
@@ -140,6 +142,8 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const float* sdf_d
   const size_t nbits = (size_t)nx * ny * g.W;
   if (int rc = h->bits.reserve(nbits)) return rc;
   if (int rc = h->status.reserve((size_t)h->nblocks * 2)) return rc;
+  if (p->algo == B200ISO_MT)
+    if (int rc = h->celloff.reserve(nbits)) return rc;
   if (int rc = h->coords.reserve((size_t)(nx + ny + nz))) return rc;
 
   if (h->timing) CU(cudaEventRecord(h->ev[0], st));
@@ -163,9 +167,9 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const float* sdf_d
   CU(cudaMemsetAsync(h->status.p, 0, (size_t)h->nblocks * 2 * sizeof(unsigned long long), st));
   CU(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int), st));
   if (p->algo == B200ISO_MC)
-    iso::count_kernel<0><<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->status.p, h->ticket, h->nblocks, h->totals_dev, totals_out);
+    iso::count_kernel<0><<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->status.p, h->ticket, h->nblocks, h->totals_dev, totals_out, nullptr);
   else
-    iso::count_kernel<1><<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->status.p, h->ticket, h->nblocks, h->totals_dev, totals_out);
+    iso::count_kernel<1><<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->status.p, h->ticket, h->nblocks, h->totals_dev, totals_out, h->celloff.p);
   CU(cudaGetLastError());
   h->launches++;
   // grid coordinates (LinRange), consumed by generate
@@ -193,6 +197,7 @@ int enqueue_generate(b200iso_handle* h, void* verts_dev, int64_t vcap, int64_t* 
     a.verts = verts_dev, a.faces = (long long*)faces_dev, a.vcap = vcap, a.fcap = fcap;
     a.vbase_dev = (const long long*)vertex_base_dev, a.vbase = vertex_base;
     a.iso_d = p.iso, a.iso_f = (float)p.iso, a.eps_d = p.eps, a.eps_f = (float)p.eps;
+    a.iso_is_f32 = p.iso_is_f32, a.eps_is_f32 = p.eps_is_f32, a.p_is_f32 = p.range_kind == B200ISO_RANGE_F32;
     const unsigned nb = (unsigned)h->nblocks;
     const bool pf32 = p.range_kind == B200ISO_RANGE_F32;
     if (p.algo == B200ISO_MC) {
@@ -201,7 +206,7 @@ int enqueue_generate(b200iso_handle* h, void* verts_dev, int64_t vcap, int64_t* 
       else if (h->vert_is_f64) iso::mc_generate_kernel<0, double><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
       else iso::mc_generate_kernel<0, float><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
     } else {
-      if (int rc = iso::launch_mt_generate(a, h->grid, p, h->vert_is_f64, nb, st)) return fail(B200ISO_EINVAL, "MT launch failed (%d)", rc);
+      if (int rc = iso::launch_mt_generate(a, h->grid, p, h->vert_is_f64, h->celloff.p, nb, st)) return fail(B200ISO_EINVAL, "MT launch failed (%d)", rc);
     }
     CU(cudaGetLastError());
     h->launches++;
@@ -251,7 +256,7 @@ int b200iso_destroy(b200iso_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  h->bits.release(), h->status.release(), h->coords.release(), h->field.release(), h->vstage.release(), h->fstage.release();
+  h->bits.release(), h->celloff.release(), h->status.release(), h->coords.release(), h->field.release(), h->vstage.release(), h->fstage.release();
   if (h->ticket) cudaFree(h->ticket);
   if (h->totals_dev) cudaFree(h->totals_dev);
   if (h->totals_host) cudaFreeHost(h->totals_host);

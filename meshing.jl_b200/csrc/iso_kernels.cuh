@@ -291,89 +291,6 @@ __device__ __forceinline__ void lookback(unsigned long long* status, long long b
 }
 
 // ------------------------------------------------------------------------------------------------------
-// (2) count + scan.  ALGO 0 = MC, 1 = MT.
-// Per-voxel counts: MC nverts = crossed cube edges, nfaces = table; MT nfaces = table, nverts = owned
-// crossed edges (table indexed by case and low-boundary flags).
-struct CountTables {
-  uint8_t nf[256];        // faces per case
-  uint8_t nown[256 * 8];  // MT only: owned crossed edges per (case, flags)
-};
-
-template <int ALGO>
-__device__ __forceinline__ void load_count_tables(uint8_t* nf_s, uint8_t* nown_s) {
-  for (int i = threadIdx.x; i < 256; i += blockDim.x)
-    nf_s[i] = ALGO == 0 ? (uint8_t)((ISO_MC_VERTS[i] >> 52) & 7) : ISO_MT_NF[i];
-  if (ALGO == 1)
-    for (int i = threadIdx.x; i < 2048; i += blockDim.x) nown_s[i] = ISO_MT_NOWN[i];
-}
-
-// vertex + face count of one cell.  For MT `flags` = low-boundary flags of the voxel column (bit0: x==0,
-// bit1: y==0); the z flag (bit2) applies to voxel z==0 only.
-template <int ALGO>
-__device__ __forceinline__ void cell_counts(const Quad& q, int i, uint32_t m, const uint8_t* nf_s, const uint8_t* nown_s,
-                                            int flags_xy, bool first_word, uint32_t& nv, uint32_t& nf) {
-  nv = 0, nf = 0;
-  if (m == 0) return;
-  if (ALGO == 0) nv = mc_nverts_masked(q, i, q.vm[i]);
-  uint32_t mm = m;
-  while (mm) {
-    const int k = __ffs(mm) - 1;
-    mm &= mm - 1;
-    const uint32_t c = case_of<ALGO>(q, i, k);
-    nf += nf_s[c];
-    if (ALGO == 1) nv += nown_s[c * 8 + (flags_xy | ((first_word && k == 0) ? 4 : 0))];
-  }
-}
-
-template <int ALGO>
-__global__ void __launch_bounds__(CB_THREADS)
-count_kernel(const uint32_t* __restrict__ bits, Grid g, unsigned long long* status, unsigned int* ticket,
-             long long nblocks, long long* totals_a, long long* totals_b) {
-  __shared__ uint8_t nf_s[256];
-  __shared__ uint8_t nown_s[ALGO == 1 ? 2048 : 1];
-  __shared__ unsigned long long red_v[CB_THREADS / 32], red_f[CB_THREADS / 32];
-  __shared__ long long sb;
-  if (threadIdx.x == 0) sb = atomicAdd(ticket, 1u);
-  load_count_tables<ALGO>(nf_s, nown_s);
-  __syncthreads();
-  const long long b = sb;
-  int x, quad0;
-  block_coords(g, b, x, quad0);
-  const int qr = quad0 + threadIdx.x;
-  uint32_t nv = 0, nf = 0;
-  if (qr < g.quads_per_row) {
-    const int y = qr / g.Wq, zq = qr - y * g.Wq;
-    Quad q;
-    load_quad(bits, g, x, y, zq, q);
-    const int flags_xy = (x == 0 ? 1 : 0) | (y == 0 ? 2 : 0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint32_t cv, cf;
-      cell_counts<ALGO>(q, i, active_mask(q, i), nf_s, nown_s, flags_xy, zq == 0 && i == 0, cv, cf);
-      nv += cv, nf += cf;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    nv += __shfl_xor_sync(0xffffffffu, nv, o);
-    nf += __shfl_xor_sync(0xffffffffu, nf, o);
-  }
-  if ((threadIdx.x & 31) == 0) red_v[threadIdx.x >> 5] = nv, red_f[threadIdx.x >> 5] = nf;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    unsigned long long av = 0, af = 0;
-#pragma unroll
-    for (int w = 0; w < CB_THREADS / 32; ++w) av += red_v[w], af += red_f[w];
-    unsigned long long ev, ef;
-    lookback(status, b, av, af, ev, ef);
-    if (b == nblocks - 1 && threadIdx.x == 0) {
-      totals_a[0] = (long long)(ev + av), totals_a[1] = (long long)(ef + af);
-      if (totals_b) totals_b[0] = (long long)(ev + av), totals_b[1] = (long long)(ef + af);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------
 // coordinates: LinRange(first, last, n)[i] = P((1-t)*a + t*b), t = i/(n-1) in Float64 (Julia Base lerpi,
 // SURVEY.md A2).  Stored as doubles (a Float32 value is exact in a double).
 __global__ void coords_kernel(double* out, int nx, int ny, int nz, double x0, double x1, double y0, double y1, double z0,
@@ -438,6 +355,7 @@ struct GenArgs {
   float iso_f;
   float eps_f;
   double eps_d;
+  int iso_is_f32, eps_is_f32, p_is_f32;  // typeof(iso), typeof(eps), eltype of the points (ranges)
 };
 
 template <int MODE>
@@ -459,7 +377,11 @@ __device__ __forceinline__ void mc_interp(const GenArgs& a, float va, float vb, 
   } else {
     const double mu = __ddiv_rn(__dsub_rn(a.iso_d, (double)va), (double)den);
 #pragma unroll
-    for (int q = 0; q < 3; ++q) out[q] = __dadd_rn(pa[q], __dmul_rn(mu, __dsub_rn(pb[q], pa[q])));
+    for (int q = 0; q < 3; ++q) {
+      // p2 .- p1 is evaluated in the points' own type before the promotion to Float64
+      const double d = a.p_is_f32 ? (double)__fsub_rn((float)pb[q], (float)pa[q]) : __dsub_rn(pb[q], pa[q]);
+      out[q] = __dadd_rn(pa[q], __dmul_rn(mu, d));
+    }
   }
 }
 

@@ -1,7 +1,354 @@
-// mt_kernels.cuh -- Marching Tetrahedra generate kernel (placeholder until the owner-rule kernel lands)
+// mt_kernels.cuh -- Marching Tetrahedra on the sign bit-field (replaces src/marching_tetrahedra.jl:11-163).
+//
+// The reference de-duplicates vertices with a Dict keyed on a global edge id (getVertId, :67-84) while it
+// sweeps the voxels sequentially.  The Dict is never iterated, so the result is fully determined by
+// "the first voxel in scan order that touches an edge creates its vertex" -- the OWNER rule
+// (SURVEY.md Appendix A7): the owner of an edge is the lexicographically smallest in-bounds voxel that
+// contains it, i.e. the voxel shifted by -1 on every axis on which both edge endpoints have offset 0.
+// Interior voxels own exactly the 7 edges that end in corner 7 = (1,1,1); voxels with index 0 on an axis
+// own the extra edges lying in that low face.  Hence, without any hash table:
+//   vertex order  = voxels in scan order, inside a voxel its owned crossed edges in first-appearance
+//                   order of its face list (table ISO_MT_OWNED[case][lowflags]),
+//   vertex count  = per 32-voxel word a handful of masked popcounts (mt_owned_masked),
+//   face indices  = offset of the owner voxel + rank of the edge in the owner's list.
 #pragma once
-#include "iso_kernels.cuh"
 #include "../../include/b200iso.h"
+#include "iso_kernels.cuh"
+
 namespace iso {
-inline int launch_mt_generate(const GenArgs&, const Grid&, const b200iso_params&, int, unsigned, cudaStream_t) { return -1; }
+
+// Crossing words of the 19 voxel edges of cell i (bit k: edge of voxel k is crossed).  Corner positions
+// (src/lut/mt.jl:23-51): word of corner (dx,dy,dz) is s<dx><dy> for dz = 0, t<dx><dy> for dz = 1.
+#define MT_E1(q, i) ((q).s00[i] ^ (q).s01[i])   // (0,0,0)-(0,1,0)  low axes x,z
+#define MT_E2(q, i) ((q).s01[i] ^ (q).s11[i])   // (0,1,0)-(1,1,0)  low z
+#define MT_E3(q, i) ((q).s10[i] ^ (q).s11[i])   // (1,0,0)-(1,1,0)  low z
+#define MT_E4(q, i) ((q).s00[i] ^ (q).s10[i])   // (0,0,0)-(1,0,0)  low y,z
+#define MT_E5(q, i) ((q).t00[i] ^ (q).t01[i])   // (0,0,1)-(0,1,1)  low x
+#define MT_E6(q, i) ((q).t01[i] ^ (q).t11[i])   // (0,1,1)-(1,1,1)
+#define MT_E7(q, i) ((q).t10[i] ^ (q).t11[i])   // (1,0,1)-(1,1,1)
+#define MT_E8(q, i) ((q).t00[i] ^ (q).t10[i])   // (0,0,1)-(1,0,1)  low y
+#define MT_E9(q, i) ((q).s00[i] ^ (q).t00[i])   // (0,0,0)-(0,0,1)  low x,y
+#define MT_E10(q, i) ((q).s01[i] ^ (q).t01[i])  // (0,1,0)-(0,1,1)  low x
+#define MT_E11(q, i) ((q).s11[i] ^ (q).t11[i])  // (1,1,0)-(1,1,1)
+#define MT_E12(q, i) ((q).s10[i] ^ (q).t10[i])  // (1,0,0)-(1,0,1)  low y
+#define MT_E13(q, i) ((q).s00[i] ^ (q).s11[i])  // (0,0,0)-(1,1,0)  low z
+#define MT_E14(q, i) ((q).s00[i] ^ (q).t10[i])  // (0,0,0)-(1,0,1)  low y
+#define MT_E15(q, i) ((q).s00[i] ^ (q).t01[i])  // (0,0,0)-(0,1,1)  low x
+#define MT_E16(q, i) ((q).t00[i] ^ (q).t11[i])  // (0,0,1)-(1,1,1)
+#define MT_E17(q, i) ((q).s01[i] ^ (q).t11[i])  // (0,1,0)-(1,1,1)
+#define MT_E18(q, i) ((q).s10[i] ^ (q).t11[i])  // (1,0,0)-(1,1,1)
+#define MT_E19(q, i) ((q).s00[i] ^ (q).t11[i])  // (0,0,0)-(1,1,1)
+
+// Number of vertices created by the voxels of cell i selected by `mask` (owned AND crossed edges).
+// fxy: bit0 = column has x == 0, bit1 = y == 0; first_word: bit 0 of this cell is the voxel z == 0.
+__device__ __forceinline__ uint32_t mt_owned_masked(const Quad& q, int i, uint32_t mask, int fxy, bool first_word) {
+  uint32_t n = __popc(MT_E6(q, i) & mask) + __popc(MT_E7(q, i) & mask) + __popc(MT_E11(q, i) & mask) +
+               __popc(MT_E16(q, i) & mask) + __popc(MT_E17(q, i) & mask) + __popc(MT_E18(q, i) & mask) +
+               __popc(MT_E19(q, i) & mask);
+  if (fxy & 1) n += __popc(MT_E5(q, i) & mask) + __popc(MT_E10(q, i) & mask) + __popc(MT_E15(q, i) & mask);
+  if (fxy & 2) n += __popc(MT_E8(q, i) & mask) + __popc(MT_E12(q, i) & mask) + __popc(MT_E14(q, i) & mask);
+  if (fxy == 3) n += __popc(MT_E9(q, i) & mask);
+  if (first_word) {
+    const uint32_t mz = mask & 1u;
+    n += __popc(MT_E2(q, i) & mz) + __popc(MT_E3(q, i) & mz) + __popc(MT_E13(q, i) & mz);
+    if (fxy & 1) n += __popc(MT_E1(q, i) & mz);
+    if (fxy & 2) n += __popc(MT_E4(q, i) & mz);
+  }
+  return n;
+}
+
+// single 32-voxel cell (x, y, zw) for owner look-ups outside the block's own quad-cells
+__device__ __forceinline__ void load_cell(const uint32_t* __restrict__ bits, const Grid& g, int x, int y, int zw, Quad& q) {
+  const uint32_t* c00 = bits + (long long)x * g.row_words + (long long)y * g.W + zw;
+  const uint32_t* c10 = c00 + g.row_words;
+  const bool more = zw + 1 < g.W;
+  const uint32_t a00 = __ldg(c00), a01 = __ldg(c00 + g.W), a10 = __ldg(c10), a11 = __ldg(c10 + g.W);
+  const uint32_t n00 = more ? __ldg(c00 + 1) : 0u, n01 = more ? __ldg(c00 + g.W + 1) : 0u;
+  const uint32_t n10 = more ? __ldg(c10 + 1) : 0u, n11 = more ? __ldg(c10 + g.W + 1) : 0u;
+  q.s00[0] = a00, q.s01[0] = a01, q.s10[0] = a10, q.s11[0] = a11;
+  q.t00[0] = __funnelshift_r(a00, n00, 1), q.t01[0] = __funnelshift_r(a01, n01, 1);
+  q.t10[0] = __funnelshift_r(a10, n10, 1), q.t11[0] = __funnelshift_r(a11, n11, 1);
+  const int rem = g.nz - 1 - zw * 32;
+  q.vm[0] = rem >= 32 ? 0xffffffffu : rem <= 0 ? 0u : ((1u << rem) - 1u);
+}
+
+// Base.max / Base.min on floats: NaN if either argument is NaN; equal arguments resolve by sign.
+template <class F>
+__device__ __forceinline__ F jl_max(F x, F y) {
+  if (x != x || y != y) return x + y;
+  if (x == y) return signbit(x) ? y : x;
+  return x > y ? x : y;
+}
+template <class F>
+__device__ __forceinline__ F jl_min(F x, F y) {
+  if (x != x || y != y) return x + y;
+  if (x == y) return signbit(x) ? x : y;
+  return x < y ? x : y;
+}
+
+constexpr int MTG_NB = CB_THREADS;       // active voxels per dense round
+constexpr int MTG_MAXV = MTG_NB * 13;    // <= 13 owned edges per voxel (boundary corner voxel)
+constexpr int MTG_MAXF = MTG_NB * 12;    // <= 12 faces per voxel
+constexpr int MTG_EDGES = 13;            // <= 13 crossed edges per voxel
+
+// A32: promote_type(typeof(iso), typeof(eps)) == Float32 (vertPos weights in Float32), else Float64.
+// P32: points (ranges) are Float32.  V: vertex element type.
+template <bool A32, bool P32, typename V>
+__global__ void __launch_bounds__(CB_THREADS)
+mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
+  __shared__ unsigned long long own0_s[256];   // ISO_MT_OWNED[c][flags = 0]
+  __shared__ unsigned long long faces_s[768];  // ISO_MT_FACES
+  __shared__ uint32_t cross_s[256];
+  __shared__ uint8_t nown0_s[256], nf_s[256];
+  __shared__ uint16_t einfo_s[20];
+  __shared__ uint8_t eshift_s[160];
+  __shared__ unsigned long long warp_s[CB_THREADS / 32];
+  __shared__ uint32_t rec_yz[MTG_NB], rec_vc[MTG_NB], rec_f[MTG_NB];
+  __shared__ int32_t evid[MTG_NB * MTG_EDGES];  // vertex id of each crossed edge, relative to the block's first vertex
+  __shared__ uint8_t owner_v[MTG_MAXV];
+  __shared__ uint8_t owner_f[MTG_MAXF];
+  __shared__ uint32_t round_nv, round_nf;
+
+  const int tid = threadIdx.x;
+  own0_s[tid] = ISO_MT_OWNED[tid * 8];
+  nown0_s[tid] = ISO_MT_NOWN[tid * 8];
+  nf_s[tid] = ISO_MT_NF[tid];
+  cross_s[tid] = ISO_MT_CROSS[tid];
+  for (int i = tid; i < 768; i += CB_THREADS) faces_s[i] = ISO_MT_FACES[i];
+  if (tid < 20) einfo_s[tid] = ISO_MT_EDGE_INFO[tid];
+  if (tid < 160) eshift_s[tid] = ISO_MT_EDGE_SHIFT[tid];
+
+  const long long b = blockIdx.x;
+  int x, quad0;
+  block_coords(g, b, x, quad0);
+  const int qr = quad0 + tid;
+  const bool live = qr < g.quads_per_row;
+  int y = 0, zq = 0;
+  uint32_t m[4] = {0, 0, 0, 0};
+  uint32_t tnv = 0, tnf = 0, tna = 0;
+  __syncthreads();
+  if (live) {
+    y = qr / g.Wq, zq = qr - y * g.Wq;
+    Quad q;
+    load_quad(a.bits, g, x, y, zq, q);
+    const int fxy = (x == 0 ? 1 : 0) | (y == 0 ? 2 : 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      m[i] = active_mask(q, i);
+      if (m[i]) {
+        tnv += mt_owned_masked(q, i, q.vm[i], fxy, zq == 0 && i == 0);
+        tna += __popc(m[i]);
+        uint32_t mm = m[i];
+        while (mm) {
+          const int k = __ffs(mm) - 1;
+          mm &= mm - 1;
+          tnf += nf_s[case_of<1>(q, i, k)];
+        }
+      }
+    }
+  }
+  unsigned long long total;
+  const unsigned long long excl = block_excl_scan(pack3(tnv, tnf, tna), warp_s, total);
+  const uint32_t blk_na = ISO_PK_A(total);
+  if (blk_na == 0) return;
+
+  unsigned long long bv = 0, bf = 0;
+  if (b > 0) {
+    bv = a.status[2 * (b - 1)] & VAL_MASK;
+    bf = a.status[2 * (b - 1) + 1] & VAL_MASK;
+  }
+  const long long vbase = a.vbase + (a.vbase_dev ? *a.vbase_dev : 0);
+  const double* xp = a.coords;
+  const double* yp = a.coords + g.nx;
+  const double* zp = a.coords + g.nx + g.ny;
+  V* verts = reinterpret_cast<V*>(a.verts);
+  const uint32_t my_a0 = ISO_PK_A(excl), my_v0 = ISO_PK_V(excl), my_f0 = ISO_PK_F(excl);
+  const int fx = x == 0 ? 1 : 0;
+
+  auto owned_word = [&](uint32_t c, int flags) -> unsigned long long {
+    return flags == 0 ? own0_s[c] : __ldg(&ISO_MT_OWNED[c * 8 + flags]);
+  };
+  auto nown_of = [&](uint32_t c, int flags) -> uint32_t {
+    return flags == 0 ? (uint32_t)nown0_s[c] : (uint32_t)__ldg(&ISO_MT_NOWN[c * 8 + flags]);
+  };
+
+  for (uint32_t lo = 0; lo < blk_na; lo += MTG_NB) {
+    const uint32_t hi = min(lo + (uint32_t)MTG_NB, blk_na);
+    // ---- B1a: records of the active voxels in [lo, hi) ----
+    if (tna && my_a0 < hi && my_a0 + tna > lo) {
+      Quad q;
+      load_quad(a.bits, g, x, y, zq, q);
+      const int fxy = fx | (y == 0 ? 2 : 0);
+      uint32_t idx = my_a0, v = my_v0, f = my_f0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t mm = m[i];
+        while (mm) {
+          const int k = __ffs(mm) - 1;
+          mm &= mm - 1;
+          const uint32_t c = case_of<1>(q, i, k);
+          const int flags = fxy | ((zq == 0 && i == 0 && k == 0) ? 4 : 0);
+          if (idx >= lo && idx < hi) {
+            const uint32_t s = idx - lo;
+            rec_yz[s] = (uint32_t)y | ((uint32_t)((zq * 4 + i) * 32 + k) << 16);
+            rec_vc[s] = v | (c << 24);
+            rec_f[s] = f;
+          }
+          v += nown_of(c, flags);
+          f += nf_s[c];
+          ++idx;
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t cnt = hi - lo;
+    const uint32_t rv0 = rec_vc[0] & 0xffffffu, rf0 = rec_f[0];
+    // ---- B1b: thread per voxel: owner maps ----
+    if ((uint32_t)tid < cnt) {
+      const uint32_t vc = rec_vc[tid], yz = rec_yz[tid];
+      const uint32_t c = vc >> 24;
+      const int flags = fx | ((yz & 0xffffu) == 0 ? 2 : 0) | ((yz >> 16) == 0 ? 4 : 0);
+      const uint32_t nv = nown_of(c, flags), nf = nf_s[c];
+      const uint32_t v0 = (vc & 0xffffffu) - rv0, f0 = rec_f[tid] - rf0;
+      for (uint32_t i = 0; i < nv; ++i) owner_v[v0 + i] = (uint8_t)tid;
+      for (uint32_t i = 0; i < nf; ++i) owner_f[f0 + i] = (uint8_t)tid;
+      if ((uint32_t)tid == cnt - 1) round_nv = v0 + nv, round_nf = f0 + nf;
+    }
+    // ---- B1c: thread per (voxel, crossed edge): resolve the vertex id through the owner voxel ----
+    for (uint32_t it = tid; it < cnt * MTG_EDGES; it += CB_THREADS) {
+      const uint32_t s = it / MTG_EDGES, j = it - s * MTG_EDGES;
+      const uint32_t vc = rec_vc[s], yz = rec_yz[s];
+      const uint32_t c = vc >> 24;
+      const uint32_t cm = cross_s[c];
+      if (j >= (uint32_t)__popc(cm)) continue;
+      const int e = __fns(cm, 0, j + 1) + 1;  // j-th crossed edge, 1..19
+      const int vy = (int)(yz & 0xffffu), vz = (int)(yz >> 16);
+      const int flags = fx | (vy == 0 ? 2 : 0) | (vz == 0 ? 4 : 0);
+      const int low = (einfo_s[e] >> 6) & 7;
+      const int sh = low & ~flags;  // axes on which the owner is the previous voxel
+      int32_t id;
+      if (sh == 0) {  // this voxel owns the edge
+        const unsigned long long ow = owned_word(c, flags);
+        int r = 0;
+        while (((ow >> (5 * r)) & 31u) != (unsigned)e) ++r;
+        id = (int32_t)(vc & 0xffffffu) + r;
+      } else {
+        const int ox = x - (sh & 1), oy = vy - ((sh >> 1) & 1), oz = vz - (sh >> 2);
+        const int eo = eshift_s[e * 8 + sh];  // the same edge in the owner's frame
+        const int oflags = (ox == 0 ? 1 : 0) | (oy == 0 ? 2 : 0) | (oz == 0 ? 4 : 0);
+        Quad q;
+        load_cell(a.bits, g, ox, oy, oz >> 5, q);
+        const int k = oz & 31;
+        const uint32_t oc = case_of<1>(q, 0, k);
+        const unsigned long long ow = owned_word(oc, oflags);
+        int r = 0;
+        while (((ow >> (5 * r)) & 31u) != (unsigned)eo) ++r;
+        // vertices created before the owner voxel: block prefix + cell prefix + in-cell prefix
+        const uint32_t below = q.vm[0] & ((1u << k) - 1u);
+        const uint32_t incell = mt_owned_masked(q, 0, below, oflags & 3, (oz >> 5) == 0);
+        const int oq = oy * g.Wq + (oz >> 7);  // quad-cell of the owner inside its x-row
+        const long long ob = (long long)ox * g.blocks_per_row + oq / CB_THREADS;
+        const unsigned long long obv = ob > 0 ? (a.status[2 * (ob - 1)] & VAL_MASK) : 0ull;
+        const uint32_t co = __ldg(celloff + (long long)ox * g.row_words + (long long)oy * g.W + (oz >> 5));
+        id = (int32_t)((long long)(obv + co + incell + r) - (long long)bv);
+      }
+      evid[s * MTG_EDGES + j] = id;
+    }
+    __syncthreads();
+    const uint32_t nvr = round_nv, nfr = round_nf;
+    const long long gv0 = (long long)bv + rv0;
+    const long long gf0 = (long long)bf + rf0;
+
+    // ---- B2: thread per vertex (vertPos, src/marching_tetrahedra.jl:42-55) ----
+    for (uint32_t k = tid; k < nvr; k += CB_THREADS) {
+      const uint32_t s = owner_v[k];
+      const uint32_t vc = rec_vc[s], yz = rec_yz[s];
+      const uint32_t c = vc >> 24;
+      const int vy = (int)(yz & 0xffffu), vz = (int)(yz >> 16);
+      const int flags = fx | (vy == 0 ? 2 : 0) | (vz == 0 ? 4 : 0);
+      const uint32_t which = k - ((vc & 0xffffffu) - rv0);
+      const int e = (int)((owned_word(c, flags) >> (5 * which)) & 31u);
+      const uint32_t info = einfo_s[e];
+      const int sx = info & 1, sy = (info >> 1) & 1, sz = (info >> 2) & 1;
+      const int tx = (info >> 3) & 1, ty = (info >> 4) & 1, tz = (info >> 5) & 1;
+      const float srcVal = __ldg(a.sdf + (x + sx) + g.ldx * (vy + sy) + g.plane * (vz + sz));
+      const float tgtVal = __ldg(a.sdf + (x + tx) + g.ldx * (vy + ty) + g.plane * (vz + tz));
+      const double bx = __ldg(xp + x), by = __ldg(yp + vy), bz = __ldg(zp + vz);
+      const double ex = __ldg(xp + x + 1), ey = __ldg(yp + vy + 1), ez = __ldg(zp + vz + 1);
+      const float den = __fsub_rn(tgtVal, srcVal);
+      double p[3];
+      const double base[3] = {bx, by, bz}, endp[3] = {ex, ey, ez};
+      const int c1[3] = {sx, sy, sz}, c2[3] = {tx, ty, tz};
+      if (A32) {
+        const float q = __fdiv_rn(__fsub_rn(a.iso_f, srcVal), den);
+        const float av = jl_min(jl_max(q, a.eps_f), __fsub_rn(1.0f, a.eps_f));
+        const float bw = __fsub_rn(1.0f, av);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float w = __fadd_rn(__fmul_rn((float)c1[d], bw), __fmul_rn((float)c2[d], av));
+          if (P32) {
+            const float dd = __fsub_rn((float)endp[d], (float)base[d]);
+            p[d] = (double)__fadd_rn((float)base[d], __fmul_rn(w, dd));
+          } else {
+            const double dd = __dsub_rn(endp[d], base[d]);
+            p[d] = __dadd_rn(base[d], __dmul_rn((double)w, dd));
+          }
+        }
+      } else {
+        const double q = a.iso_is_f32 ? (double)__fdiv_rn(__fsub_rn(a.iso_f, srcVal), den)
+                                      : __ddiv_rn(__dsub_rn(a.iso_d, (double)srcVal), (double)den);
+        const double epsd = a.eps_is_f32 ? (double)a.eps_f : a.eps_d;
+        const double hi1 = a.eps_is_f32 ? (double)__fsub_rn(1.0f, a.eps_f) : __dsub_rn(1.0, a.eps_d);
+        const double av = jl_min(jl_max(q, epsd), hi1);
+        const double bw = __dsub_rn(1.0, av);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const double w = __dadd_rn(__dmul_rn((double)c1[d], bw), __dmul_rn((double)c2[d], av));
+          const double dd = P32 ? (double)__fsub_rn((float)endp[d], (float)base[d]) : __dsub_rn(endp[d], base[d]);
+          p[d] = __dadd_rn(base[d], __dmul_rn(w, dd));
+        }
+      }
+      const long long gi = gv0 + k;
+      if (gi < a.vcap) {
+        V* o = verts + 3 * gi;
+        o[0] = (V)p[0], o[1] = (V)p[1], o[2] = (V)p[2];
+      }
+    }
+    // ---- B3: thread per face ----
+    for (uint32_t k = tid; k < nfr; k += CB_THREADS) {
+      const uint32_t s = owner_f[k];
+      const uint32_t c = rec_vc[s] >> 24;
+      const uint32_t fi = k - (rec_f[s] - rf0);
+      const uint32_t cm = cross_s[c];
+      const long long gi = gf0 + k;
+      if (gi < a.fcap) {
+        long long* o = a.faces + 3 * gi;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const uint32_t slot = 3 * fi + j;
+          const uint32_t e = (uint32_t)(faces_s[c * 3 + slot / 12] >> (5 * (slot % 12))) & 31u;
+          const uint32_t es = __popc(cm & ((1u << (e - 1)) - 1u));
+          o[j] = vbase + (long long)bv + evid[s * MTG_EDGES + es] + 1;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+inline int launch_mt_generate(const GenArgs& a, const Grid& g, const b200iso_params& p, int vert_is_f64, const uint32_t* celloff,
+                              unsigned nb, cudaStream_t st) {
+  const bool a32 = p.iso_is_f32 && p.eps_is_f32;
+  const bool p32 = p.range_kind == B200ISO_RANGE_F32;
+  if (a32) {
+    if (p32) mt_generate_kernel<true, true, float><<<nb, CB_THREADS, 0, st>>>(a, g, celloff);
+    else if (vert_is_f64) mt_generate_kernel<true, false, double><<<nb, CB_THREADS, 0, st>>>(a, g, celloff);
+    else mt_generate_kernel<true, false, float><<<nb, CB_THREADS, 0, st>>>(a, g, celloff);
+  } else {
+    if (p32) mt_generate_kernel<false, true, double><<<nb, CB_THREADS, 0, st>>>(a, g, celloff);
+    else mt_generate_kernel<false, false, double><<<nb, CB_THREADS, 0, st>>>(a, g, celloff);
+  }
+  return 0;
+}
+
 }  // namespace iso
