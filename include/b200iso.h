@@ -57,6 +57,12 @@ typedef struct b200iso_params {
   double iso;
   double eps;         /* MT only (default 1e-3) */
   double x0, x1, y0, y1, z0, z1;
+  /* x-slab sharding (MC): the field passed to count is the slab of samples
+   * [x_offset, x_offset + nx) of a volume with nx_global samples along x, and x0/x1 are the endpoints of
+   * the WHOLE volume, so that slab vertices get exactly the coordinates of the unsharded call
+   * (LinRange(first(X), last(X), nx_global)[x_offset + i]).  Both 0 for an unsharded call. */
+  int64_t x_offset;
+  int64_t nx_global;
 } b200iso_params;
 
 /* ---- lifetime ------------------------------------------------------------------------------------ */

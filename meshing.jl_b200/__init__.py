@@ -10,3 +10,5 @@ declared in include/b200iso.h; there is no CPU fallback.
 from . import synth  # noqa: F401
 from .api import MarchingCubes, MarchingTetrahedra, isosurface, Float32, Float64  # noqa: F401
 from . import capi  # noqa: F401
+from . import sharding  # noqa: F401
+from . import api  # noqa: F401

@@ -173,6 +173,36 @@ def _isosurface_torch(t, params, device):
     return verts, faces
 
 
+def isosurface_slab(sdf_slab, method, x_offset, nx_global, vertex_base, *ranges, device=0):
+    """One rank's share of a sharded Marching Cubes call: `sdf_slab` holds samples [x_offset, x_offset+nx) of
+    a volume with nx_global samples along x; `ranges` are X, Y, Z of the WHOLE volume.  Returns the slab's
+    (vertices, faces) with `vertex_base` already added to the face indices.  Two-phase use
+    (count -> all-gather -> generate) is `slab_count` + `slab_generate`."""
+    h, nv, nf, f64 = slab_count(sdf_slab, method, x_offset, nx_global, *ranges, device=device)
+    return slab_generate(h, nv, nf, f64, vertex_base)
+
+
+def slab_count(sdf_slab, method, x_offset, nx_global, *ranges, device=0):
+    a = np.asfortranarray(np.asarray(sdf_slab))
+    if a.dtype != np.float32 or a.ndim != 3:
+        raise TypeError("3-D Float32 field expected")
+    if not isinstance(method, MarchingCubes):
+        raise TypeError("x-slab sharding is implemented for MarchingCubes (MT runs as replicas)")
+    params = make_params(method, *ranges)
+    params.x_offset, params.nx_global = x_offset, nx_global
+    nx, ny, nz = a.shape
+    h = get_handle(device)
+    nv, nf, f64 = h.count(params, a.ctypes.data, capi.HOST, nx, ny, nz, nx)
+    return h, nv, nf, f64
+
+
+def slab_generate(h, nv, nf, f64, vertex_base):
+    verts = np.empty((nv, 3), dtype=np.float64 if f64 else np.float32)
+    faces = np.empty((nf, 3), dtype=np.int64)
+    h.generate(verts.ctypes.data, faces.ctypes.data, capi.HOST, vertex_base)
+    return verts, faces
+
+
 def case_indices(sdf, method=None, device=0):
     """Per-voxel case index (_get_cubeindex, src/common.jl:10-20) in scan-rank order, computed on the GPU
     from the classify kernel's bit-field (parity check hook)."""

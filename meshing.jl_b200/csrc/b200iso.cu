@@ -90,11 +90,28 @@ struct b200iso_handle {
   long long nblocks = 0;
   int vert_is_f64 = 0;
   long long nverts = 0, nfaces = 0;
-  // timing
+  // timing: a ring of per-step event sets, read back (averaged) only when b200iso_timings is called
+  static constexpr int NSLOT = 256;
+  enum { E_C0, E_C1, E_C2, E_G0, E_G1, E_H0, E_H1, E_D0, E_D1, E_N };
   bool timing = false;
-  cudaEvent_t ev[8] = {};
-  float ms[5] = {0, 0, 0, 0, 0};
+  cudaEvent_t* ev = nullptr;          // [NSLOT][E_N], created lazily
+  unsigned char* ev_set = nullptr;    // which events of a slot were recorded
+  long long step = 0;                 // steps (count calls) since timing was enabled
   int64_t launches = 0;
+  int rec(int which) {
+    if (!timing) return 0;
+    const int slot = (int)((step > 0 ? step - 1 : 0) % NSLOT);
+    cudaError_t e = cudaEventRecord(ev[slot * E_N + which], stream);
+    if (e != cudaSuccess) return fail(B200ISO_ECUDA, "cudaEventRecord: %s", cudaGetErrorString(e));
+    ev_set[slot * E_N + which] = 1;
+    return 0;
+  }
+  void begin_step() {
+    if (!timing) return;
+    ++step;
+    const int slot = (int)((step - 1) % NSLOT);
+    for (int i = 0; i < E_N; ++i) ev_set[slot * E_N + i] = 0;
+  }
 };
 
 namespace {
@@ -111,11 +128,15 @@ int check_params(const b200iso_params* p, int64_t nx, int64_t ny, int64_t nz, in
   if (nx < 0 || ny < 0 || nz < 0) return fail(B200ISO_EINVAL, "negative dimension");
   if (ldx < nx) return fail(B200ISO_EINVAL, "ldx (%lld) < nx (%lld)", (long long)ldx, (long long)nx);
   if (nx > 65536 || ny > 65536 || nz > 65536) return fail(B200ISO_EINVAL, "dimension larger than 65536 is not supported");
+  if (p->nx_global != 0 || p->x_offset != 0) {
+    if (p->algo != B200ISO_MC) return fail(B200ISO_EINVAL, "x-slab sharding is implemented for MarchingCubes only");
+    if (p->x_offset < 0 || p->nx_global < p->x_offset + nx) return fail(B200ISO_EINVAL, "slab [x_offset, x_offset+nx) outside nx_global");
+  }
   return 0;
 }
 
 int enqueue_count(b200iso_handle* h, const b200iso_params* p, const float* sdf_dev, int64_t nx, int64_t ny, int64_t nz,
-                  int64_t ldx, long long* totals_out) {
+                  int64_t ldx, long long* totals_out, bool step_begun = false) {
   cudaStream_t st = h->stream;
   h->prm = *p;
   h->sdf_dev = sdf_dev;
@@ -146,7 +167,8 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const float* sdf_d
     if (int rc = h->celloff.reserve(nbits)) return rc;
   if (int rc = h->coords.reserve((size_t)(nx + ny + nz))) return rc;
 
-  if (h->timing) CU(cudaEventRecord(h->ev[0], st));
+  if (!step_begun) h->begin_step();
+  if (int rc = h->rec(b200iso_handle::E_C0)) return rc;
   // (1) sign-pack
   {
     const bool vec = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(sdf_dev) & 15) == 0);
@@ -162,7 +184,7 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const float* sdf_d
     CU(cudaGetLastError());
     h->launches++;
   }
-  if (h->timing) CU(cudaEventRecord(h->ev[1], st));
+  if (int rc = h->rec(b200iso_handle::E_C1)) return rc;
   // (2) count + decoupled look-back scan
   CU(cudaMemsetAsync(h->status.p, 0, (size_t)h->nblocks * 2 * sizeof(unsigned long long), st));
   CU(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int), st));
@@ -176,11 +198,12 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const float* sdf_d
   {
     const int n = (int)(nx + ny + nz);
     iso::coords_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->coords.p, g.nx, g.ny, g.nz, p->x0, p->x1, p->y0, p->y1, p->z0, p->z1,
-                                                        p->range_kind == B200ISO_RANGE_F32);
+                                                        p->range_kind == B200ISO_RANGE_F32, (int)p->x_offset,
+                                                        (int)(p->nx_global > 0 ? p->nx_global : nx));
     CU(cudaGetLastError());
     h->launches++;
   }
-  if (h->timing) CU(cudaEventRecord(h->ev[2], st));
+  if (int rc = h->rec(b200iso_handle::E_C2)) return rc;
   h->counted = true;
   return 0;
 }
@@ -189,7 +212,7 @@ int enqueue_generate(b200iso_handle* h, void* verts_dev, int64_t vcap, int64_t* 
                      const int64_t* vertex_base_dev, int64_t vertex_base) {
   if (!h->counted) return fail(B200ISO_ESTATE, "generate called before count");
   cudaStream_t st = h->stream;
-  if (h->timing) CU(cudaEventRecord(h->ev[3], st));
+  if (int rc = h->rec(b200iso_handle::E_G0)) return rc;
   if (h->nblocks > 0) {
     const b200iso_params& p = h->prm;
     iso::GenArgs a{};
@@ -211,7 +234,7 @@ int enqueue_generate(b200iso_handle* h, void* verts_dev, int64_t vcap, int64_t* 
     CU(cudaGetLastError());
     h->launches++;
   }
-  if (h->timing) CU(cudaEventRecord(h->ev[4], st));
+  if (int rc = h->rec(b200iso_handle::E_G1)) return rc;
   return 0;
 }
 
@@ -247,7 +270,6 @@ int b200iso_create(b200iso_handle** out, int device) {
   CU(cudaMalloc((void**)&h->ticket, sizeof(unsigned int)));
   CU(cudaMalloc((void**)&h->totals_dev, 2 * sizeof(long long)));
   CU(cudaMallocHost((void**)&h->totals_host, 2 * sizeof(long long)));
-  for (auto& e : h->ev) CU(cudaEventCreate(&e));
   *out = h;
   return 0;
 }
@@ -260,8 +282,11 @@ int b200iso_destroy(b200iso_handle* h) {
   if (h->ticket) cudaFree(h->ticket);
   if (h->totals_dev) cudaFree(h->totals_dev);
   if (h->totals_host) cudaFreeHost(h->totals_host);
-  for (auto& e : h->ev)
-    if (e) cudaEventDestroy(e);
+  if (h->ev) {
+    for (int i = 0; i < b200iso_handle::NSLOT * b200iso_handle::E_N; ++i) cudaEventDestroy(h->ev[i]);
+    delete[] h->ev;
+    delete[] h->ev_set;
+  }
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return 0;
@@ -310,31 +335,23 @@ int b200iso_count(b200iso_handle* h, const b200iso_params* p, const float* sdf, 
   CU(cudaSetDevice(h->device));
   const float* dev = sdf;
   int64_t dldx = ldx;
-  h->ms[3] = 0;
-  if (mem == B200ISO_HOST && nx * ny * nz > 0) {
+  const bool staged = mem == B200ISO_HOST && nx * ny * nz > 0;
+  if (staged) {
     // stage with a 16-byte aligned leading dimension so the 128-bit load path always applies
     dldx = (nx + 3) / 4 * 4;
     if (int rc = h->field.reserve((size_t)dldx * ny * nz)) return rc;
-    if (h->timing) CU(cudaEventRecord(h->ev[5], h->stream));
+    h->begin_step();
+    if (int rc = h->rec(b200iso_handle::E_H0)) return rc;
     if (dldx == ldx)
       CU(cudaMemcpyAsync(h->field.p, sdf, (size_t)ldx * ny * nz * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     else
       CU(cudaMemcpy2DAsync(h->field.p, (size_t)dldx * sizeof(float), sdf, (size_t)ldx * sizeof(float), (size_t)nx * sizeof(float),
                            (size_t)ny * nz, cudaMemcpyHostToDevice, h->stream));
-    if (h->timing) CU(cudaEventRecord(h->ev[6], h->stream));
+    if (int rc = h->rec(b200iso_handle::E_H1)) return rc;
     dev = h->field.p;
   }
-  if (int rc = enqueue_count(h, p, dev, nx, ny, nz, dldx, nullptr)) return rc;
+  if (int rc = enqueue_count(h, p, dev, nx, ny, nz, dldx, nullptr, staged)) return rc;
   if (int rc = fetch_totals(h)) return rc;
-  if (h->timing) {
-    if (h->nblocks > 0) {
-      cudaEventElapsedTime(&h->ms[0], h->ev[0], h->ev[1]);
-      cudaEventElapsedTime(&h->ms[1], h->ev[1], h->ev[2]);
-      if (mem == B200ISO_HOST) cudaEventElapsedTime(&h->ms[3], h->ev[5], h->ev[6]);
-    } else {
-      h->ms[0] = h->ms[1] = 0;
-    }
-  }
   if (nverts) *nverts = h->nverts;
   if (nfaces) *nfaces = h->nfaces;
   if (vert_is_f64) *vert_is_f64 = h->vert_is_f64;
@@ -348,7 +365,6 @@ int b200iso_generate(b200iso_handle* h, void* verts, int64_t* faces, int mem, in
   if (int rc = fetch_totals(h)) return rc;
   const size_t vsz = h->vert_is_f64 ? 8 : 4;
   if ((h->nverts > 0 && !verts) || (h->nfaces > 0 && !faces)) return fail(B200ISO_EINVAL, "output pointer is NULL");
-  h->ms[4] = 0;
   if (mem == B200ISO_DEVICE) {
     if (int rc = enqueue_generate(h, verts, h->nverts, faces, h->nfaces, nullptr, vertex_base)) return rc;
     CU(cudaStreamSynchronize(h->stream));
@@ -356,14 +372,12 @@ int b200iso_generate(b200iso_handle* h, void* verts, int64_t* faces, int mem, in
     if (int rc = h->vstage.reserve((size_t)h->nverts * 3 * vsz + 16)) return rc;
     if (int rc = h->fstage.reserve((size_t)h->nfaces * 3 + 2)) return rc;
     if (int rc = enqueue_generate(h, h->vstage.p, h->nverts, (int64_t*)h->fstage.p, h->nfaces, nullptr, vertex_base)) return rc;
-    if (h->timing) CU(cudaEventRecord(h->ev[5], h->stream));
+    if (int rc = h->rec(b200iso_handle::E_D0)) return rc;
     if (h->nverts) CU(cudaMemcpyAsync(verts, h->vstage.p, (size_t)h->nverts * 3 * vsz, cudaMemcpyDeviceToHost, h->stream));
     if (h->nfaces) CU(cudaMemcpyAsync(faces, h->fstage.p, (size_t)h->nfaces * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
-    if (h->timing) CU(cudaEventRecord(h->ev[6], h->stream));
+    if (int rc = h->rec(b200iso_handle::E_D1)) return rc;
     CU(cudaStreamSynchronize(h->stream));
-    if (h->timing) cudaEventElapsedTime(&h->ms[4], h->ev[5], h->ev[6]);
   }
-  if (h->timing) cudaEventElapsedTime(&h->ms[2], h->ev[3], h->ev[4]);
   return 0;
 }
 
@@ -395,13 +409,38 @@ int b200iso_case_indices(b200iso_handle* h, uint8_t* out, int mem) {
 
 int b200iso_enable_timing(b200iso_handle* h, int on) {
   if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  CU(cudaSetDevice(h->device));
+  if (on && !h->ev) {
+    const int n = b200iso_handle::NSLOT * b200iso_handle::E_N;
+    h->ev = new cudaEvent_t[n];
+    h->ev_set = new unsigned char[n]();
+    for (int i = 0; i < n; ++i) CU(cudaEventCreate(&h->ev[i]));
+  }
   h->timing = on != 0;
+  h->step = 0;
   return 0;
 }
 
 int b200iso_timings(b200iso_handle* h, float* ms, int n) {
   if (!h || !ms) return fail(B200ISO_EINVAL, "NULL argument");
-  for (int i = 0; i < n && i < 5; ++i) ms[i] = h->ms[i];
+  using H = b200iso_handle;
+  double sum[5] = {0, 0, 0, 0, 0};
+  long long cnt[5] = {0, 0, 0, 0, 0};
+  if (h->ev && h->step > 0) {
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    const long long nsteps = h->step < H::NSLOT ? h->step : H::NSLOT;
+    static const int span[5][2] = {{H::E_C0, H::E_C1}, {H::E_C1, H::E_C2}, {H::E_G0, H::E_G1}, {H::E_H0, H::E_H1}, {H::E_D0, H::E_D1}};
+    for (long long s = 0; s < nsteps; ++s)
+      for (int k = 0; k < 5; ++k) {
+        const int a = (int)s * H::E_N + span[k][0], b = (int)s * H::E_N + span[k][1];
+        if (!h->ev_set[a] || !h->ev_set[b]) continue;
+        float t = 0;
+        if (cudaEventElapsedTime(&t, h->ev[a], h->ev[b]) == cudaSuccess) sum[k] += t, cnt[k]++;
+      }
+    cudaGetLastError();
+  }
+  for (int i = 0; i < n && i < 5; ++i) ms[i] = cnt[i] ? (float)(sum[i] / cnt[i]) : 0.f;
   return 0;
 }
 

@@ -294,12 +294,12 @@ __device__ __forceinline__ void lookback(unsigned long long* status, long long b
 // coordinates: LinRange(first, last, n)[i] = P((1-t)*a + t*b), t = i/(n-1) in Float64 (Julia Base lerpi,
 // SURVEY.md A2).  Stored as doubles (a Float32 value is exact in a double).
 __global__ void coords_kernel(double* out, int nx, int ny, int nz, double x0, double x1, double y0, double y1, double z0,
-                              double z1, int f32) {
+                              double z1, int f32, int x_offset, int nx_global) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nx + ny + nz) return;
   int n, k;
   double a, b;
-  if (i < nx) n = nx, k = i, a = x0, b = x1;
+  if (i < nx) n = nx_global, k = i + x_offset, a = x0, b = x1;  // slab of a larger volume: global index
   else if (i < nx + ny) n = ny, k = i - nx, a = y0, b = y1;
   else n = nz, k = i - nx - ny, a = z0, b = z1;
   if (f32) a = (double)(float)a, b = (double)(float)b;

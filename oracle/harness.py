@@ -33,7 +33,7 @@ def lib():
         L = ctypes.CDLL(so)
         i64, dbl, vp, ci = ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_int
         L.oracle_isosurface.restype = vp
-        L.oracle_isosurface.argtypes = [ci, vp, ci, i64, i64, i64, dbl, ci, dbl, ci, dbl, dbl, dbl, dbl, dbl, dbl, ci, ci]
+        L.oracle_isosurface.argtypes = [ci, vp, ci, i64, i64, i64, dbl, ci, dbl, ci, dbl, dbl, dbl, dbl, dbl, dbl, ci, ci, i64, i64]
         L.oracle_nverts.restype = i64
         L.oracle_nverts.argtypes = [vp]
         L.oracle_nfaces.restype = i64
@@ -67,19 +67,24 @@ def _field(sdf):
 
 
 def isosurface(sdf, algo=MC, iso=0.0, iso_is_f32=False, eps=1e-3, eps_is_f32=False,
-               ranges=None, range_kind=RANGE_INT, nthreads=1):
+               ranges=None, range_kind=RANGE_INT, nthreads=1, xrange=None, copy=True):
     """Oracle isosurface.  `ranges` = ((x0,x1),(y0,y1),(z0,z1)) endpoints (default (-1,1)^3).
+    `xrange` = (xlo, xhi) restricts the MC sweep to voxel x-planes [xlo, xhi) (bounded bench sample; face
+    indices are then relative to the first vertex of the range).  `copy=False` returns only the counts.
     Returns (vertices[nv,3] float32|float64, faces[nf,3] int64 1-based)."""
-    a = _field(sdf)
+    a = sdf if (isinstance(sdf, np.ndarray) and sdf.flags.f_contiguous) else _field(sdf)
+    xlo, xhi = xrange if xrange is not None else (-1, -1)
     nx, ny, nz = a.shape
     if ranges is None:
         ranges = ((-1.0, 1.0),) * 3
     (x0, x1), (y0, y1), (z0, z1) = ranges
     L = lib()
     h = L.oracle_isosurface(algo, a.ctypes.data, int(a.dtype == np.float64), nx, ny, nz, float(iso), int(iso_is_f32),
-                            float(eps), int(eps_is_f32), x0, x1, y0, y1, z0, z1, range_kind, nthreads)
+                            float(eps), int(eps_is_f32), x0, x1, y0, y1, z0, z1, range_kind, nthreads, xlo, xhi)
     try:
         nv, nf = L.oracle_nverts(h), L.oracle_nfaces(h)
+        if not copy:
+            return nv, nf
         vt = np.float64 if L.oracle_vert_is_f64(h) else np.float32
         verts = np.empty((nv, 3), dtype=vt)
         faces = np.empty((nf, 3), dtype=np.int64)

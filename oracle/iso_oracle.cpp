@@ -150,24 +150,29 @@ void mc_sweep(const T* sdf, int64_t nx, int64_t ny, int64_t nz, I iso, const Lin
 
 template <class T, class I, class P, class V>
 void run_mc(const T* sdf, int64_t nx, int64_t ny, int64_t nz, I iso, double x0, double x1, double y0,
-            double y1, double z0, double z1, int nthreads, Result& out) {
+            double y1, double z0, double z1, int nthreads, int64_t xlo, int64_t xhi, Result& out) {
   LinRange<P> xp(x0, x1, nx), yp(y0, y1, ny), zp(z0, z1, nz);
   std::vector<V>& vts = verts_of<V>(out);
   out.vert_is_f64 = std::is_same<V, double>::value;
   if (nx < 2 || ny < 2 || nz < 2) return;
+  // [xlo, xhi): voxel x-planes to sweep (bench: a bounded sample of a large field, same strides as the
+  // full sweep); the whole volume is [0, nx-1).
+  if (xlo < 0) xlo = 0;
+  if (xhi < 0 || xhi > nx - 1) xhi = nx - 1;
+  if (xhi <= xlo) return;
   if (nthreads <= 1) {
-    mc_sweep<T, I, P, V>(sdf, nx, ny, nz, iso, xp, yp, zp, 0, nx - 1, vts, out.faces);
+    mc_sweep<T, I, P, V>(sdf, nx, ny, nz, iso, xp, yp, zp, xlo, xhi, vts, out.faces);
     return;
   }
   // x-slab threaded driver (bench CPU arm only): each thread runs the same sweep on its x-range,
   // results are concatenated in x order with face indices rebased -- byte-identical to 1 thread.
-  int64_t nvx = nx - 1;
+  int64_t nvx = xhi - xlo;
   if (nthreads > nvx) nthreads = (int)nvx;
   std::vector<std::vector<V>> pv(nthreads);
   std::vector<std::vector<int64_t>> pf(nthreads);
   std::vector<std::thread> th;
   for (int t = 0; t < nthreads; ++t) {
-    int64_t xa = nvx * t / nthreads, xb = nvx * (t + 1) / nthreads;
+    int64_t xa = xlo + nvx * t / nthreads, xb = xlo + nvx * (t + 1) / nthreads;
     th.emplace_back([&, t, xa, xb] { mc_sweep<T, I, P, V>(sdf, nx, ny, nz, iso, xp, yp, zp, xa, xb, pv[t], pf[t]); });
   }
   for (auto& t : th) t.join();
@@ -301,6 +306,7 @@ struct Args {
   double x0, x1, y0, y1, z0, z1;
   int range_kind;
   int nthreads;
+  int64_t xlo, xhi;  // MC only: voxel x-plane range, -1 = whole volume
 };
 
 template <class T, class I, class E, class P>
@@ -311,9 +317,9 @@ void dispatch_v(const Args& a, Result& out) {
              (a.algo == 1 && std::is_same<E, double>::value);
   if (a.algo == 0) {
     if (f64)
-      run_mc<T, I, P, double>((const T*)a.sdf, a.nx, a.ny, a.nz, (I)a.iso, a.x0, a.x1, a.y0, a.y1, a.z0, a.z1, a.nthreads, out);
+      run_mc<T, I, P, double>((const T*)a.sdf, a.nx, a.ny, a.nz, (I)a.iso, a.x0, a.x1, a.y0, a.y1, a.z0, a.z1, a.nthreads, a.xlo, a.xhi, out);
     else
-      run_mc<T, I, P, float>((const T*)a.sdf, a.nx, a.ny, a.nz, (I)a.iso, a.x0, a.x1, a.y0, a.y1, a.z0, a.z1, a.nthreads, out);
+      run_mc<T, I, P, float>((const T*)a.sdf, a.nx, a.ny, a.nz, (I)a.iso, a.x0, a.x1, a.y0, a.y1, a.z0, a.z1, a.nthreads, a.xlo, a.xhi, out);
   } else {
     if (f64)
       run_mt<T, I, E, P, double>((const T*)a.sdf, a.nx, a.ny, a.nz, (I)a.iso, (E)a.eps, a.x0, a.x1, a.y0, a.y1, a.z0, a.z1, out);
@@ -362,8 +368,8 @@ extern "C" {
 // Runs the restated isosurface(); returns an opaque result (free with oracle_free).
 void* oracle_isosurface(int algo, const void* sdf, int sdf_is_f64, int64_t nx, int64_t ny, int64_t nz, double iso,
                         int iso_is_f32, double eps, int eps_is_f32, double x0, double x1, double y0, double y1,
-                        double z0, double z1, int range_kind, int nthreads) {
-  Args a{algo, sdf, sdf_is_f64, nx, ny, nz, iso, iso_is_f32, eps, eps_is_f32, x0, x1, y0, y1, z0, z1, range_kind, nthreads};
+                        double z0, double z1, int range_kind, int nthreads, int64_t xlo, int64_t xhi) {
+  Args a{algo, sdf, sdf_is_f64, nx, ny, nz, iso, iso_is_f32, eps, eps_is_f32, x0, x1, y0, y1, z0, z1, range_kind, nthreads, xlo, xhi};
   Result* r = new Result();
   if (sdf_is_f64) dispatch_i<double>(a, *r);
   else dispatch_i<float>(a, *r);

@@ -224,3 +224,28 @@ def test_parity_config_512_gyroid(pkg, oracle, algo):
     v, f = _check(pkg, oracle, s, algo)
     if algo == "MC":
         assert abs(len(v) - 10123197) < 2000 and abs(len(f) - 5061727) < 1000  # SURVEY.md Appendix C estimates
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_slabs_equal_unsharded(pkg, oracle, world):
+    """N x-slabs (each with its halo plane, run through the GPU one after the other like N ranks) stitched
+    with the exclusive prefix of their counts == the unsharded mesh, byte for byte."""
+    shape = (70, 33, 45)
+    s = pkg.synth.gyroid(shape)
+    m = pkg.MarchingCubes(iso=pkg.Float32(0.05))
+    X, Y, Z = (0, 3), (-1, 1), (2, 5)
+    v1, f1 = pkg.isosurface(s, m, X, Y, Z)
+    vo, fo = oracle.isosurface(s, 0, iso=0.05, iso_is_f32=True, ranges=(X, Y, Z))
+    assert np.array_equal(f1, fo) and _bits_equal(v1, vo)
+    counts, slabs = [], []
+    for r in range(world):
+        xa, xb = pkg.sharding.slab_bounds(shape[0], world, r)
+        slabs.append((xa, xb))
+        _, nv, nf, _ = pkg.api.slab_count(s[xa:xb], m, xa, shape[0], X, Y, Z)
+        counts.append((nv, nf))
+    parts = []
+    for r, (xa, xb) in enumerate(slabs):
+        vb, _ = pkg.sharding.exclusive_bases(counts, r)
+        parts.append(pkg.api.isosurface_slab(s[xa:xb], m, xa, shape[0], vb, X, Y, Z))
+    v, f = pkg.sharding.stitch(parts)
+    assert np.array_equal(f, f1) and _bits_equal(v, v1)
