@@ -73,8 +73,10 @@ int b200iso_destroy(b200iso_handle* h);
 const char* b200iso_last_error(void);
 /* Library/ABI version (major*1000 + minor). */
 int b200iso_version(void);
-/* Run on the caller's CUDA stream (a cudaStream_t); NULL restores the handle's own stream. */
+/* Run on the caller's CUDA stream (a cudaStream_t, used as is: NULL is CUDA's legacy default stream).
+ * b200iso_use_own_stream switches back to the stream the handle created for itself. */
 int b200iso_set_stream(b200iso_handle* h, void* cuda_stream);
+int b200iso_use_own_stream(b200iso_handle* h);
 
 /* ---- the drop-in pair: replaces the body of isosurface(sdf, method, X, Y, Z) ---------------------------
  * b200iso_count   : classify + count + scan.  `sdf` is Float32, host or device (mem), nx*ny*nz samples with

@@ -170,6 +170,7 @@ def _isosurface_torch(t, params, device):
         verts = torch.empty((nv, 3), dtype=torch.float64 if f64 else torch.float32, device=t.device)
         faces = torch.empty((nf, 3), dtype=torch.int64, device=t.device)
         h.generate(verts.data_ptr(), faces.data_ptr(), capi.DEVICE, 0)
+        h.use_own_stream()
     return verts, faces
 
 

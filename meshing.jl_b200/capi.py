@@ -63,6 +63,7 @@ def load():
     L.b200iso_last_error.argtypes = []
     L.b200iso_version.argtypes = []
     L.b200iso_set_stream.argtypes = [vp, vp]
+    L.b200iso_use_own_stream.argtypes = [vp]
     L.b200iso_count.argtypes = [vp, pp, vp, ci, i64, i64, i64, i64, pi64, pi64, pci]
     L.b200iso_generate.argtypes = [vp, vp, vp, ci, i64]
     L.b200iso_count_async.argtypes = [vp, pp, vp, i64, i64, i64, i64, vp]
@@ -103,7 +104,11 @@ class Handle:
             pass
 
     def set_stream(self, cuda_stream_ptr):
+        """Run on the given cudaStream_t (0 = CUDA's legacy default stream, e.g. torch's default stream)."""
         _check(self.L.b200iso_set_stream(self.h, ctypes.c_void_p(cuda_stream_ptr or 0)))
+
+    def use_own_stream(self):
+        _check(self.L.b200iso_use_own_stream(self.h))
 
     def count(self, params, sdf_ptr, mem, nx, ny, nz, ldx):
         nv, nf, f64 = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()

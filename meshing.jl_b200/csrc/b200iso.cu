@@ -143,15 +143,7 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const float* sdf_d
   h->vert_is_f64 = vertex_is_f64(*p);
   h->counted = false, h->totals_known = false;
   iso::Grid& g = h->grid;
-  g.nx = (int)nx, g.ny = (int)ny, g.nz = (int)nz;
-  g.ldx = ldx, g.plane = (long long)ldx * ny;
-  const int words = (int)((nz + 31) / 32);
-  g.W = (words + 3) / 4 * 4;
-  if (g.W == 0) g.W = 4;
-  g.Wq = g.W / 4;
-  g.row_words = (long long)ny * g.W;
-  g.quads_per_row = (int)((ny > 0 ? ny - 1 : 0) * g.Wq);
-  g.blocks_per_row = (g.quads_per_row + iso::CB_THREADS - 1) / iso::CB_THREADS;
+  iso::grid_setup(g, nx, ny, nz, ldx);
   h->nblocks = (nx > 1 && ny > 1 && nz > 1) ? (long long)(nx - 1) * g.blocks_per_row : 0;
 
   if (h->nblocks == 0) {  // a dimension < 2: zero voxels, empty mesh (src/marching_cubes.jl:40)
@@ -294,7 +286,13 @@ int b200iso_destroy(b200iso_handle* h) {
 
 int b200iso_set_stream(b200iso_handle* h, void* cuda_stream) {
   if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
-  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  h->stream = (cudaStream_t)cuda_stream;
+  return 0;
+}
+
+int b200iso_use_own_stream(b200iso_handle* h) {
+  if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  h->stream = h->own_stream;
   return 0;
 }
 

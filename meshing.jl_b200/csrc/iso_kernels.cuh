@@ -28,20 +28,67 @@
 namespace iso {
 
 // ------------------------------------------------------------------------------------------------------
-// problem geometry shared by count / generate / case kernels
+// problem geometry and the block/thread -> voxel mapping shared by count / generate
+//
+// Unit of work: the quad-cell = 4 consecutive z-words = 128 z-consecutive voxels of one voxel column (x,y).
+// A block owns whole columns (so its voxels are one contiguous range of the reference's scan order):
+// CGB groups of 32 adjacent columns of one x-row.  LANES RUN ACROSS COLUMNS (y), warps across z: the 32
+// lanes of a warp look at the same z-range of 32 neighbouring columns, which the surface crosses either
+// in most of them or in none -- so a warp can skip an empty region with one vote, and the per-voxel loops
+// of its lanes have similar trip counts.
 struct Grid {
   int nx, ny, nz;        // samples
   int W;                 // words per sample column (multiple of 4, >= ceil(nz/32))
   int Wq;                // W / 4 : quad-cells per column
-  int quads_per_row;     // (ny-1) * Wq : quad-cells of one voxel x-row, in scan order (y, z)
-  int blocks_per_row;    // ceil(quads_per_row / CB_THREADS)
+  int WZ;                // warps along z per column group: min(Wq, 8)
+  int QPT;               // quad-cells per thread: ceil(Wq / WZ) (consecutive in z)
+  int CGB;               // 32-column groups per block: 8 / WZ
+  int cols_per_block;    // 32 * CGB
+  int blocks_per_row;    // ceil((ny-1) / cols_per_block)
   long long row_words;   // ny * W : words between sample column (x,y) and (x+1,y)
   long long ldx;         // field leading dimension (elements)
   long long plane;       // ldx * ny
 };
 
-constexpr int CB_THREADS = 256;            // threads per count/generate block
-constexpr int CB_CELLS = CB_THREADS * 4;   // 32-voxel cells per block
+constexpr int CB_THREADS = 256;  // threads per count/generate block (8 warps)
+
+inline void grid_setup(Grid& g, long long nx, long long ny, long long nz, long long ldx) {
+  g.nx = (int)nx, g.ny = (int)ny, g.nz = (int)nz;
+  g.ldx = ldx, g.plane = ldx * ny;
+  const int words = (int)((nz + 31) / 32);
+  g.W = (words + 3) / 4 * 4;
+  if (g.W == 0) g.W = 4;
+  g.Wq = g.W / 4;
+  g.WZ = g.Wq < 8 ? g.Wq : 8;
+  g.QPT = (g.Wq + g.WZ - 1) / g.WZ;
+  g.CGB = 8 / g.WZ;
+  g.cols_per_block = 32 * g.CGB;
+  g.row_words = ny * g.W;
+  g.blocks_per_row = (int)(((ny > 0 ? ny - 1 : 0) + g.cols_per_block - 1) / g.cols_per_block);
+}
+
+// what one thread of block b works on
+struct TMap {
+  int x, y;          // voxel column
+  int zq_lo, zq_hi;  // its quad-cells [zq_lo, zq_hi)
+  int ord;           // position of the thread in the block's scan order (column-major, z-minor), 0..255
+  bool live;
+};
+
+__device__ __forceinline__ TMap thread_map(const Grid& g, long long b) {
+  TMap m;
+  m.x = (int)(b / g.blocks_per_row);
+  const int cb = (int)(b - (long long)m.x * g.blocks_per_row);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cg = w / g.WZ, wz = w - cg * g.WZ;
+  m.y = cb * g.cols_per_block + cg * 32 + lane;
+  m.zq_lo = wz * g.QPT;
+  m.zq_hi = min(g.Wq, m.zq_lo + g.QPT);
+  m.live = cg < g.CGB && m.y < g.ny - 1 && m.zq_lo < m.zq_hi;
+  const int used = g.CGB * g.WZ * 32;  // threads that own a slot of the scan order
+  m.ord = cg < g.CGB ? (cg * 32 + lane) * g.WZ + wz : used + ((int)threadIdx.x - used);
+  return m;
+}
 
 // ------------------------------------------------------------------------------------------------------
 // (1) signpack
@@ -171,8 +218,10 @@ __device__ __forceinline__ void shift_up(const uint4 a, uint32_t nxt, uint32_t* 
   t[3] = __funnelshift_r(a.w, nxt, 1);
 }
 
-// Loads the quad-cell (x, y, zq) from the bit-field.
-__device__ __forceinline__ void load_quad(const uint32_t* __restrict__ bits, const Grid& g, int x, int y, int zq, Quad& q) {
+// Loads the quad-cell (x, y, zq) from the bit-field.  Returns false -- without building the shifted words --
+// when no sign changes anywhere in its 4x(128+1) samples (cheap test on the raw words): then no voxel of
+// the quad-cell is active.
+__device__ __forceinline__ bool load_quad(const uint32_t* __restrict__ bits, const Grid& g, int x, int y, int zq, Quad& q) {
   const uint32_t* c00 = bits + (long long)x * g.row_words + (long long)y * g.W + zq * 4;
   const uint32_t* c10 = c00 + g.row_words;
   const bool more = zq + 1 < g.Wq;
@@ -182,6 +231,14 @@ __device__ __forceinline__ void load_quad(const uint32_t* __restrict__ bits, con
   const uint4 a11 = __ldg(reinterpret_cast<const uint4*>(c10 + g.W));
   const uint32_t n00 = more ? __ldg(c00 + 4) : 0u, n01 = more ? __ldg(c00 + g.W + 4) : 0u;
   const uint32_t n10 = more ? __ldg(c10 + 4) : 0u, n11 = more ? __ldg(c10 + g.W + 4) : 0u;
+  // bits of samples beyond nz are 0, so an all-ones run that reaches the padding reads as "mixed" here;
+  // that only costs the slow path, the exact valid-mask is applied below.
+  const uint32_t nb = (n00 & n01 & n10 & n11 & 1u) ? 0xffffffffu : ((n00 | n01 | n10 | n11) & 1u ? 0x1u : 0u);
+  const uint32_t any = a00.x | a00.y | a00.z | a00.w | a01.x | a01.y | a01.z | a01.w | a10.x | a10.y | a10.z | a10.w |
+                       a11.x | a11.y | a11.z | a11.w | (nb & 1u);
+  const uint32_t all = a00.x & a00.y & a00.z & a00.w & a01.x & a01.y & a01.z & a01.w & a10.x & a10.y & a10.z & a10.w &
+                       a11.x & a11.y & a11.z & a11.w & (more ? nb : 0xffffffffu);
+  if (any == 0u || all == 0xffffffffu) return false;
   shift_up(a00, n00, q.s00, q.t00);
   shift_up(a01, n01, q.s01, q.t01);
   shift_up(a10, n10, q.s10, q.t10);
@@ -191,6 +248,7 @@ __device__ __forceinline__ void load_quad(const uint32_t* __restrict__ bits, con
     const int rem = g.nz - 1 - (zq * 4 + i) * 32;  // voxels z .. valid iff z < nz-1
     q.vm[i] = rem >= 32 ? 0xffffffffu : rem <= 0 ? 0u : ((1u << rem) - 1u);
   }
+  return true;
 }
 
 __device__ __forceinline__ uint32_t active_mask(const Quad& q, int i) {
@@ -211,7 +269,7 @@ __device__ __forceinline__ uint32_t case_of(const Quad& q, int i, int k) {
 }
 
 // MC: vertices of a voxel = its sign-changing cube edges (popcount(edge_table[c]) == nverts, App. B)
-// -> the per-cell vertex total and every in-cell prefix is 12 masked popcounts.
+// -> the per-cell vertex total is 12 masked popcounts.
 __device__ __forceinline__ uint32_t mc_nverts_masked(const Quad& q, int i, uint32_t mask) {
   uint32_t n = __popc((q.s00[i] ^ q.s10[i]) & mask) + __popc((q.s10[i] ^ q.s11[i]) & mask) +
                __popc((q.s11[i] ^ q.s01[i]) & mask) + __popc((q.s01[i] ^ q.s00[i]) & mask);
@@ -222,10 +280,39 @@ __device__ __forceinline__ uint32_t mc_nverts_masked(const Quad& q, int i, uint3
   return n;
 }
 
-// block -> (x, first quad of the row chunk)
-__device__ __forceinline__ void block_coords(const Grid& g, long long b, int& x, int& quad0) {
-  x = (int)(b / g.blocks_per_row);
-  quad0 = (int)(b - (long long)x * g.blocks_per_row) * CB_THREADS;
+// ---- block scans (256 threads) ---------------------------------------------------------------------------
+// exclusive scan in thread order; s_w: 8 words of shared scratch.  Contains two barriers.
+__device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* s_w, uint32_t& total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();  // s_w may still be read by the previous scan
+  if (lane == 31) s_w[w] = inc;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < CB_THREADS / 32; ++i) {
+    const uint32_t t = s_w[i];
+    if (i < w) base += t;
+    tot += t;
+  }
+  total = tot;
+  return base + inc - v;
+}
+
+// exclusive scan in the block's SCAN ORDER (TMap::ord): values are transposed through s_val[256]
+__device__ __forceinline__ uint32_t block_excl_scan_ord(uint32_t v, int ord, uint32_t* s_val, uint32_t* s_w, uint32_t& total) {
+  s_val[ord] = v;
+  __syncthreads();
+  const uint32_t u = s_val[threadIdx.x];
+  const uint32_t e = block_excl_scan_u32(u, s_w, total);
+  s_val[threadIdx.x] = e;
+  __syncthreads();
+  return s_val[ord];
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -385,171 +472,138 @@ __device__ __forceinline__ void mc_interp(const GenArgs& a, float va, float vb, 
   }
 }
 
-// packed block-scan element: nverts bits 0..23, nfaces bits 24..43, active voxels bits 44..59
-__device__ __forceinline__ unsigned long long pack3(uint32_t nv, uint32_t nf, uint32_t na) {
-  return (unsigned long long)nv | ((unsigned long long)nf << 24) | ((unsigned long long)na << 44);
-}
-#define ISO_PK_V(p) ((uint32_t)((p) & 0xffffffull))
-#define ISO_PK_F(p) ((uint32_t)(((p) >> 24) & 0xfffffull))
-#define ISO_PK_A(p) ((uint32_t)(((p) >> 44) & 0xffffull))
+constexpr int GEN_NB = CB_THREADS;     // active voxels per dense round (one per thread)
+constexpr int GEN_MAXV = GEN_NB * 12;  // vertices of a round (MC: <= 12 per voxel)
+constexpr int GEN_MAXF = GEN_NB * 5;   // faces of a round (MC: <= 5 per voxel)
 
-// exclusive block scan of one packed value per thread; returns the exclusive prefix, `total` = block sum
-__device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long v, unsigned long long* warp_s,
-                                                              unsigned long long& total) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  unsigned long long inc = v;
+// Pushes the (y,z | case) records of this thread's active voxels whose position in the block's scan order
+// falls in [lo, hi).  `a0` = position of the thread's first active voxel.
+template <int ALGO>
+__device__ __forceinline__ void push_records(const uint32_t* __restrict__ bits, const Grid& g, const TMap& tm, uint32_t a0,
+                                             uint32_t lo, uint32_t hi, uint32_t* rec_yz, uint8_t* rec_c) {
+  uint32_t idx = a0;
+  for (int zq = tm.zq_lo; zq < tm.zq_hi && idx < hi; ++zq) {
+    Quad q;
+    if (!load_quad(bits, g, tm.x, tm.y, zq, q)) continue;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
+    for (int i = 0; i < 4; ++i) {
+      uint32_t mm = active_mask(q, i);
+      if (idx + __popc(mm) <= lo) {  // whole cell before the window
+        idx += __popc(mm);
+        continue;
+      }
+      while (mm) {
+        const int k = __ffs(mm) - 1;
+        mm &= mm - 1;
+        if (idx >= lo && idx < hi) {
+          const uint32_t s = idx - lo;
+          rec_yz[s] = (uint32_t)tm.y | ((uint32_t)((zq * 4 + i) * 32 + k) << 16);
+          rec_c[s] = (uint8_t)case_of<ALGO>(q, i, k);
+        }
+        ++idx;
+      }
+    }
   }
-  if (lane == 31) warp_s[w] = inc;
-  __syncthreads();
-  unsigned long long base = 0, tot = 0;
-#pragma unroll
-  for (int i = 0; i < CB_THREADS / 32; ++i) {
-    const unsigned long long t = warp_s[i];
-    if (i < w) base += t;
-    tot += t;
-  }
-  total = tot;
-  return base + inc - v;
 }
 
-constexpr int GEN_NB = CB_THREADS;         // active voxels per dense round (one per thread)
-constexpr int GEN_MAXV = GEN_NB * 12;      // vertices of a round (MC: <= 12 per voxel)
-constexpr int GEN_MAXF = GEN_NB * 5;       // faces of a round (MC: <= 5 per voxel)
+// number of active voxels of this thread's quad-cells
+__device__ __forceinline__ uint32_t count_active(const uint32_t* __restrict__ bits, const Grid& g, const TMap& tm) {
+  uint32_t na = 0;
+  if (tm.live)
+    for (int zq = tm.zq_lo; zq < tm.zq_hi; ++zq) {
+      Quad q;
+      if (!load_quad(bits, g, tm.x, tm.y, zq, q)) continue;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) na += __popc(active_mask(q, i));
+    }
+  return na;
+}
 
 template <int MODE, typename V>
-__global__ void __launch_bounds__(CB_THREADS)
+__global__ void __launch_bounds__(CB_THREADS, 4)
 mc_generate_kernel(GenArgs a, Grid g) {
   __shared__ unsigned long long tabV[256], tabF[256];
-  __shared__ unsigned long long warp_s[CB_THREADS / 32];
-  __shared__ uint32_t rec_yz[GEN_NB], rec_vc[GEN_NB], rec_f[GEN_NB];
+  __shared__ uint32_t s_val[CB_THREADS], s_w[CB_THREADS / 32];
+  __shared__ uint32_t rec_yz[GEN_NB];
+  __shared__ uint16_t rec_v[GEN_NB], rec_f[GEN_NB];
+  __shared__ uint8_t rec_c[GEN_NB];
+  __shared__ float corner[GEN_NB][8];
   __shared__ uint8_t owner_v[GEN_MAXV], owner_f[GEN_MAXF];
   __shared__ uint8_t edge_c[12];
 
   const int tid = threadIdx.x;
+  const long long b = blockIdx.x;
+  const TMap tm = thread_map(g, b);
+  // ---- A: active voxels per thread, exclusive scan in scan order ----
+  const uint32_t tna = count_active(a.bits, g, tm);
+  uint32_t blk_na;
+  const uint32_t my_a0 = block_excl_scan_ord(tna, tm.ord, s_val, s_w, blk_na);
+  if (blk_na == 0) return;  // uniform: nothing crosses this block
+
   tabV[tid] = ISO_MC_VERTS[tid];
   tabF[tid] = ISO_MC_FACES[tid];
   if (tid < 12) edge_c[tid] = ISO_MC_EDGE_CORNERS[tid];
-
-  const long long b = blockIdx.x;
-  int x, quad0;
-  block_coords(g, b, x, quad0);
-  const int qr = quad0 + tid;
-  const bool live = qr < g.quads_per_row;
-  int y = 0, zq = 0;
-  uint32_t m[4] = {0, 0, 0, 0};
-  uint32_t tnv = 0, tnf = 0, tna = 0;
-  __syncthreads();  // tables visible
-  if (live) {
-    y = qr / g.Wq, zq = qr - y * g.Wq;
-    Quad q;
-    load_quad(a.bits, g, x, y, zq, q);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      m[i] = active_mask(q, i);
-      if (m[i]) {
-        tnv += mc_nverts_masked(q, i, q.vm[i]);
-        tna += __popc(m[i]);
-        uint32_t mm = m[i];
-        while (mm) {
-          const int k = __ffs(mm) - 1;
-          mm &= mm - 1;
-          tnf += (uint32_t)((tabV[case_of<0>(q, i, k)] >> 52) & 7);
-        }
-      }
-    }
-  }
-  unsigned long long total;
-  const unsigned long long excl = block_excl_scan(pack3(tnv, tnf, tna), warp_s, total);
-  const uint32_t blk_na = ISO_PK_A(total);
-  if (blk_na == 0) return;  // uniform
-
-  // exclusive prefixes of this block in the whole mesh
+  // exclusive prefixes of this block in the whole mesh (published by count_kernel)
   unsigned long long bv = 0, bf = 0;
   if (b > 0) {
     bv = a.status[2 * (b - 1)] & VAL_MASK;
     bf = a.status[2 * (b - 1) + 1] & VAL_MASK;
   }
   const long long vbase = a.vbase + (a.vbase_dev ? *a.vbase_dev : 0);
-  const double* xp = a.coords;
   const double* yp = a.coords + g.nx;
   const double* zp = a.coords + g.nx + g.ny;
+  const double x0d = __ldg(a.coords + tm.x), x1d = __ldg(a.coords + tm.x + 1);
   V* verts = reinterpret_cast<V*>(a.verts);
-
-  const uint32_t my_a0 = ISO_PK_A(excl), my_v0 = ISO_PK_V(excl), my_f0 = ISO_PK_F(excl);
+  const int x = tm.x;
 
   for (uint32_t lo = 0; lo < blk_na; lo += GEN_NB) {
     const uint32_t hi = min(lo + (uint32_t)GEN_NB, blk_na);
-    // ---- B1a: owners of the quad-cells push the records of their voxels that fall in [lo, hi) ----
-    if (tna && my_a0 < hi && my_a0 + tna > lo) {
-      Quad q;
-      load_quad(a.bits, g, x, y, zq, q);
-      uint32_t idx = my_a0, v = my_v0, f = my_f0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint32_t mm = m[i];
-        while (mm) {
-          const int k = __ffs(mm) - 1;
-          mm &= mm - 1;
-          const uint32_t c = case_of<0>(q, i, k);
-          const unsigned long long tv = tabV[c];
-          if (idx >= lo && idx < hi) {
-            const uint32_t s = idx - lo;
-            rec_yz[s] = (uint32_t)y | ((uint32_t)((zq * 4 + i) * 32 + k) << 16);
-            rec_vc[s] = v | (c << 24);
-            rec_f[s] = f;
-          }
-          v += (uint32_t)((tv >> 48) & 15);
-          f += (uint32_t)((tv >> 52) & 7);
-          ++idx;
-        }
-      }
-    }
-    __syncthreads();
     const uint32_t cnt = hi - lo;
-    const uint32_t rv0 = rec_vc[0] & 0xffffffu, rf0 = rec_f[0];
-    // ---- B1b: thread per voxel: expand owner maps ----
-    uint32_t last_v = 0, last_f = 0;
+    // ---- B1a: records (position, case) of the window's voxels, in scan order ----
+    if (tna && my_a0 < hi && my_a0 + tna > lo) push_records<0>(a.bits, g, tm, my_a0, lo, hi, rec_yz, rec_c);
+    __syncthreads();
+    // ---- B1b: thread per voxel: counts -> scan -> owner maps; gather the 8 corner samples ----
+    uint32_t nv = 0, nf = 0;
     if ((uint32_t)tid < cnt) {
-      const uint32_t vc = rec_vc[tid];
-      const unsigned long long tv = tabV[vc >> 24];
-      const uint32_t nv = (uint32_t)((tv >> 48) & 15), nf = (uint32_t)((tv >> 52) & 7);
-      const uint32_t v0 = (vc & 0xffffffu) - rv0, f0 = rec_f[tid] - rf0;
+      const unsigned long long tv = tabV[rec_c[tid]];
+      nv = (uint32_t)((tv >> 48) & 15), nf = (uint32_t)((tv >> 52) & 7);
+      const uint32_t yz = rec_yz[tid];
+      const float* p = a.sdf + x + g.ldx * (long long)(yz & 0xffffu) + g.plane * (long long)(yz >> 16);
+      const float c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + g.ldx + 1), c3 = __ldg(p + g.ldx);
+      const float* p1 = p + g.plane;
+      const float c4 = __ldg(p1), c5 = __ldg(p1 + 1), c6 = __ldg(p1 + g.ldx + 1), c7 = __ldg(p1 + g.ldx);
+      *reinterpret_cast<float4*>(&corner[tid][0]) = make_float4(c0, c1, c2, c3);
+      *reinterpret_cast<float4*>(&corner[tid][4]) = make_float4(c4, c5, c6, c7);
+    }
+    uint32_t wtot;
+    const uint32_t ex = block_excl_scan_u32(nv | (nf << 16), s_w, wtot);
+    if ((uint32_t)tid < cnt) {
+      const uint32_t v0 = ex & 0xffffu, f0 = ex >> 16;
+      rec_v[tid] = (uint16_t)v0, rec_f[tid] = (uint16_t)f0;
       for (uint32_t i = 0; i < nv; ++i) owner_v[v0 + i] = (uint8_t)tid;
       for (uint32_t i = 0; i < nf; ++i) owner_f[f0 + i] = (uint8_t)tid;
-      last_v = v0 + nv, last_f = f0 + nf;
     }
-    // round totals = end of the last voxel of the round
-    __shared__ uint32_t round_nv, round_nf;
-    if ((uint32_t)tid == cnt - 1) round_nv = last_v, round_nf = last_f;
     __syncthreads();
-    const uint32_t nvr = round_nv, nfr = round_nf;
-    const long long gv0 = (long long)bv + rv0;  // index of the round's first vertex in this slab's buffer
-    const long long gf0 = (long long)bf + rf0;
+    const uint32_t nvr = wtot & 0xffffu, nfr = wtot >> 16;
 
-    // ---- B2: thread per vertex ----
+    // ---- B2: thread per vertex (vertex_interp, src/marching_cubes.jl:100-104) ----
     for (uint32_t k = tid; k < nvr; k += CB_THREADS) {
       const uint32_t s = owner_v[k];
-      const uint32_t vc = rec_vc[s], yz = rec_yz[s];
-      const uint32_t c = vc >> 24;
-      const uint32_t which = k - ((vc & 0xffffffu) - rv0);
+      const uint32_t c = rec_c[s], yz = rec_yz[s];
+      const uint32_t which = k - rec_v[s];
       const uint32_t e = (uint32_t)(tabV[c] >> (4 * which)) & 15u;
       const uint32_t cc = edge_c[e];
+      const uint32_t ca = cc & 15u, cb = cc >> 4;
       // MC corner offsets (dx | dy<<1 | dz<<2) for corners 0..7: 0,1,3,2,4,5,7,6
-      const uint32_t oa = (0x67542310u >> (4 * (cc & 15u))) & 7u, ob = (0x67542310u >> (4 * (cc >> 4))) & 7u;
+      const uint32_t oa = (0x67542310u >> (4 * ca)) & 7u, ob = (0x67542310u >> (4 * cb)) & 7u;
+      const float va = corner[s][ca], vb = corner[s][cb];
       const int vy = (int)(yz & 0xffffu), vz = (int)(yz >> 16);
-      const int ax = x + (int)(oa & 1u), ay = vy + (int)((oa >> 1) & 1u), az = vz + (int)(oa >> 2);
-      const int bx = x + (int)(ob & 1u), by = vy + (int)((ob >> 1) & 1u), bz = vz + (int)(ob >> 2);
-      const float va = __ldg(a.sdf + ax + g.ldx * ay + g.plane * az);
-      const float vb = __ldg(a.sdf + bx + g.ldx * by + g.plane * bz);
-      const double pa[3] = {__ldg(xp + ax), __ldg(yp + ay), __ldg(zp + az)};
-      const double pb[3] = {__ldg(xp + bx), __ldg(yp + by), __ldg(zp + bz)};
+      const double y0d = __ldg(yp + vy), y1d = __ldg(yp + vy + 1), z0d = __ldg(zp + vz), z1d = __ldg(zp + vz + 1);
+      const double pa[3] = {(oa & 1u) ? x1d : x0d, (oa & 2u) ? y1d : y0d, (oa & 4u) ? z1d : z0d};
+      const double pb[3] = {(ob & 1u) ? x1d : x0d, (ob & 2u) ? y1d : y0d, (ob & 4u) ? z1d : z0d};
       double p[3];
       mc_interp<MODE>(a, va, vb, pa, pb, p);
-      const long long gi = gv0 + k;
+      const long long gi = (long long)bv + k;
       if (gi < a.vcap) {
         V* o = verts + 3 * gi;
         o[0] = (V)p[0], o[1] = (V)p[1], o[2] = (V)p[2];
@@ -558,16 +612,16 @@ mc_generate_kernel(GenArgs a, Grid g) {
     // ---- B3: thread per face ----
     for (uint32_t k = tid; k < nfr; k += CB_THREADS) {
       const uint32_t s = owner_f[k];
-      const uint32_t vc = rec_vc[s];
-      const uint32_t fi = k - (rec_f[s] - rf0);
-      const uint32_t tri = (uint32_t)(tabF[vc >> 24] >> (12 * fi)) & 0xfffu;
-      const long long fct = vbase + (long long)bv + (vc & 0xffffffu) + 1;  // 1-based index of the voxel's first vertex
-      const long long gi = gf0 + k;
+      const uint32_t fi = k - rec_f[s];
+      const uint32_t tri = (uint32_t)(tabF[rec_c[s]] >> (12 * fi)) & 0xfffu;
+      const long long fct = vbase + (long long)bv + rec_v[s] + 1;  // 1-based index of the voxel's first vertex
+      const long long gi = (long long)bf + k;
       if (gi < a.fcap) {
         long long* o = a.faces + 3 * gi;
         o[0] = fct + (tri & 15u), o[1] = fct + ((tri >> 4) & 15u), o[2] = fct + ((tri >> 8) & 15u);
       }
     }
+    bv += nvr, bf += nfr;  // next window continues where this one ended
     __syncthreads();
   }
 }

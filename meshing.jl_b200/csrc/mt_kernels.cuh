@@ -102,12 +102,12 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
   __shared__ uint8_t nown0_s[256], nf_s[256];
   __shared__ uint16_t einfo_s[20];
   __shared__ uint8_t eshift_s[160];
-  __shared__ unsigned long long warp_s[CB_THREADS / 32];
+  __shared__ uint32_t s_val[CB_THREADS], s_w[CB_THREADS / 32];
   __shared__ uint32_t rec_yz[MTG_NB], rec_vc[MTG_NB], rec_f[MTG_NB];
+  __shared__ uint8_t rec_c[MTG_NB];
   __shared__ int32_t evid[MTG_NB * MTG_EDGES];  // vertex id of each crossed edge, relative to the block's first vertex
   __shared__ uint8_t owner_v[MTG_MAXV];
   __shared__ uint8_t owner_f[MTG_MAXF];
-  __shared__ uint32_t round_nv, round_nf;
 
   const int tid = threadIdx.x;
   own0_s[tid] = ISO_MT_OWNED[tid * 8];
@@ -119,37 +119,12 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
   if (tid < 160) eshift_s[tid] = ISO_MT_EDGE_SHIFT[tid];
 
   const long long b = blockIdx.x;
-  int x, quad0;
-  block_coords(g, b, x, quad0);
-  const int qr = quad0 + tid;
-  const bool live = qr < g.quads_per_row;
-  int y = 0, zq = 0;
-  uint32_t m[4] = {0, 0, 0, 0};
-  uint32_t tnv = 0, tnf = 0, tna = 0;
-  __syncthreads();
-  if (live) {
-    y = qr / g.Wq, zq = qr - y * g.Wq;
-    Quad q;
-    load_quad(a.bits, g, x, y, zq, q);
-    const int fxy = (x == 0 ? 1 : 0) | (y == 0 ? 2 : 0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      m[i] = active_mask(q, i);
-      if (m[i]) {
-        tnv += mt_owned_masked(q, i, q.vm[i], fxy, zq == 0 && i == 0);
-        tna += __popc(m[i]);
-        uint32_t mm = m[i];
-        while (mm) {
-          const int k = __ffs(mm) - 1;
-          mm &= mm - 1;
-          tnf += nf_s[case_of<1>(q, i, k)];
-        }
-      }
-    }
-  }
-  unsigned long long total;
-  const unsigned long long excl = block_excl_scan(pack3(tnv, tnf, tna), warp_s, total);
-  const uint32_t blk_na = ISO_PK_A(total);
+  const TMap tm = thread_map(g, b);
+  const int x = tm.x;
+  // ---- A: active voxels per thread, exclusive scan in scan order ----
+  const uint32_t tna = count_active(a.bits, g, tm);
+  uint32_t blk_na;
+  const uint32_t my_a0 = block_excl_scan_ord(tna, tm.ord, s_val, s_w, blk_na);
   if (blk_na == 0) return;
 
   unsigned long long bv = 0, bf = 0;
@@ -162,8 +137,8 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
   const double* yp = a.coords + g.nx;
   const double* zp = a.coords + g.nx + g.ny;
   V* verts = reinterpret_cast<V*>(a.verts);
-  const uint32_t my_a0 = ISO_PK_A(excl), my_v0 = ISO_PK_V(excl), my_f0 = ISO_PK_F(excl);
   const int fx = x == 0 ? 1 : 0;
+  uint32_t wv = 0;  // vertices of the block emitted by previous windows
 
   auto owned_word = [&](uint32_t c, int flags) -> unsigned long long {
     return flags == 0 ? own0_s[c] : __ldg(&ISO_MT_OWNED[c * 8 + flags]);
@@ -174,46 +149,28 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
 
   for (uint32_t lo = 0; lo < blk_na; lo += MTG_NB) {
     const uint32_t hi = min(lo + (uint32_t)MTG_NB, blk_na);
-    // ---- B1a: records of the active voxels in [lo, hi) ----
-    if (tna && my_a0 < hi && my_a0 + tna > lo) {
-      Quad q;
-      load_quad(a.bits, g, x, y, zq, q);
-      const int fxy = fx | (y == 0 ? 2 : 0);
-      uint32_t idx = my_a0, v = my_v0, f = my_f0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint32_t mm = m[i];
-        while (mm) {
-          const int k = __ffs(mm) - 1;
-          mm &= mm - 1;
-          const uint32_t c = case_of<1>(q, i, k);
-          const int flags = fxy | ((zq == 0 && i == 0 && k == 0) ? 4 : 0);
-          if (idx >= lo && idx < hi) {
-            const uint32_t s = idx - lo;
-            rec_yz[s] = (uint32_t)y | ((uint32_t)((zq * 4 + i) * 32 + k) << 16);
-            rec_vc[s] = v | (c << 24);
-            rec_f[s] = f;
-          }
-          v += nown_of(c, flags);
-          f += nf_s[c];
-          ++idx;
-        }
-      }
-    }
-    __syncthreads();
     const uint32_t cnt = hi - lo;
-    const uint32_t rv0 = rec_vc[0] & 0xffffffu, rf0 = rec_f[0];
-    // ---- B1b: thread per voxel: owner maps ----
+    // ---- B1a: records (position, case) of the window's voxels, in scan order ----
+    if (tna && my_a0 < hi && my_a0 + tna > lo) push_records<1>(a.bits, g, tm, my_a0, lo, hi, rec_yz, rec_c);
+    __syncthreads();
+    // ---- B1b: thread per voxel: counts -> scan -> owner maps ----
+    uint32_t nv = 0, nf = 0;
     if ((uint32_t)tid < cnt) {
-      const uint32_t vc = rec_vc[tid], yz = rec_yz[tid];
-      const uint32_t c = vc >> 24;
+      const uint32_t c = rec_c[tid], yz = rec_yz[tid];
       const int flags = fx | ((yz & 0xffffu) == 0 ? 2 : 0) | ((yz >> 16) == 0 ? 4 : 0);
-      const uint32_t nv = nown_of(c, flags), nf = nf_s[c];
-      const uint32_t v0 = (vc & 0xffffffu) - rv0, f0 = rec_f[tid] - rf0;
+      nv = nown_of(c, flags), nf = nf_s[c];
+    }
+    uint32_t wtot;
+    const uint32_t ex = block_excl_scan_u32(nv | (nf << 16), s_w, wtot);
+    if ((uint32_t)tid < cnt) {
+      const uint32_t v0 = ex & 0xffffu, f0 = ex >> 16;
+      rec_vc[tid] = (wv + v0) | ((uint32_t)rec_c[tid] << 24);  // vertex offset relative to the block's first vertex
+      rec_f[tid] = f0;
       for (uint32_t i = 0; i < nv; ++i) owner_v[v0 + i] = (uint8_t)tid;
       for (uint32_t i = 0; i < nf; ++i) owner_f[f0 + i] = (uint8_t)tid;
-      if ((uint32_t)tid == cnt - 1) round_nv = v0 + nv, round_nf = f0 + nf;
     }
+    __syncthreads();
+    const uint32_t rv0 = wv, rf0 = 0;
     // ---- B1c: thread per (voxel, crossed edge): resolve the vertex id through the owner voxel ----
     for (uint32_t it = tid; it < cnt * MTG_EDGES; it += CB_THREADS) {
       const uint32_t s = it / MTG_EDGES, j = it - s * MTG_EDGES;
@@ -246,8 +203,7 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
         // vertices created before the owner voxel: block prefix + cell prefix + in-cell prefix
         const uint32_t below = q.vm[0] & ((1u << k) - 1u);
         const uint32_t incell = mt_owned_masked(q, 0, below, oflags & 3, (oz >> 5) == 0);
-        const int oq = oy * g.Wq + (oz >> 7);  // quad-cell of the owner inside its x-row
-        const long long ob = (long long)ox * g.blocks_per_row + oq / CB_THREADS;
+        const long long ob = (long long)ox * g.blocks_per_row + oy / g.cols_per_block;  // the owner's block
         const unsigned long long obv = ob > 0 ? (a.status[2 * (ob - 1)] & VAL_MASK) : 0ull;
         const uint32_t co = __ldg(celloff + (long long)ox * g.row_words + (long long)oy * g.W + (oz >> 5));
         id = (int32_t)((long long)(obv + co + incell + r) - (long long)bv);
@@ -255,9 +211,9 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
       evid[s * MTG_EDGES + j] = id;
     }
     __syncthreads();
-    const uint32_t nvr = round_nv, nfr = round_nf;
+    const uint32_t nvr = wtot & 0xffffu, nfr = wtot >> 16;
     const long long gv0 = (long long)bv + rv0;
-    const long long gf0 = (long long)bf + rf0;
+    const long long gf0 = (long long)bf;
 
     // ---- B2: thread per vertex (vertPos, src/marching_tetrahedra.jl:42-55) ----
     for (uint32_t k = tid; k < nvr; k += CB_THREADS) {
@@ -332,6 +288,7 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
         }
       }
     }
+    wv += nvr, bf += nfr;
     __syncthreads();
   }
 }
