@@ -286,9 +286,11 @@ def main():
     sharded = world > 1 and not spec.get("replicas")
 
     def step():
+        # classify -> count + decoupled look-back scan -> [all-gather of the slab totals] -> generate; all asynchronous
         h.count_async(params, field.data_ptr(), nxl, ny, nz, ldx, totals.data_ptr())
         if sharded:
-            # the one exchange of the sharded path: every slab's (nverts, nfaces), 16 bytes per rank
+            # the one exchange of the sharded path: every slab's (nverts, nfaces), 16 bytes per rank; its
+            # exclusive prefix is this slab's global vertex base, added to the slab's face indices in generate
             dist.all_gather_into_tensor(gathered.view(-1), totals)
             torch.sum(gathered[:rank, 0], dim=0, keepdim=True, out=vbase)
         h.generate_async(verts.data_ptr(), verts.shape[0], faces.data_ptr(), faces.shape[0], vbase.data_ptr() if sharded else 0, 0)

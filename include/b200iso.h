@@ -105,6 +105,23 @@ int b200iso_generate_async(b200iso_handle* h, void* verts_dev, int64_t vcap, int
                            const int64_t* vertex_base_dev, int64_t vertex_base);
 int b200iso_totals(b200iso_handle* h, int64_t* nverts, int64_t* nfaces, int* vert_is_f64);
 
+/* ---- single-pass form (device-resident, capacity known up front) ----------------------------------------
+ * b200iso_extract_async: the whole isosurface() in one enqueue -- classify, then ONE kernel that counts,
+ *                        scans (decoupled look-back) and generates -- into device buffers of capacity
+ *                        vcap vertices / fcap faces.  Elements beyond capacity are dropped, the true totals
+ *                        are written to totals_dev (device int64[2], may be NULL) and kept for
+ *                        b200iso_totals, so a caller that guessed too small re-allocates and calls again.
+ *                        Face indices get vertex_base + (vertex_base_dev ? *vertex_base_dev : 0).
+ *                        (Marching Tetrahedra runs its count and generate kernels back to back instead.)
+ * b200iso_add_vertex_base_async: adds *vertex_base_dev to the first min(totals_dev[1], fcap) faces -- the
+ *                        sharded fix-up when the slab's global vertex base (from the all-gather of the
+ *                        slabs' totals) becomes known only after the slab was extracted. */
+int b200iso_extract_async(b200iso_handle* h, const b200iso_params* p, const float* sdf_dev, int64_t nx, int64_t ny,
+                          int64_t nz, int64_t ldx, void* verts_dev, int64_t vcap, int64_t* faces_dev, int64_t fcap,
+                          const int64_t* vertex_base_dev, int64_t vertex_base, int64_t* totals_dev);
+int b200iso_add_vertex_base_async(b200iso_handle* h, int64_t* faces_dev, int64_t fcap, const int64_t* totals_dev,
+                                  const int64_t* vertex_base_dev);
+
 /* ---- parity / introspection ----------------------------------------------------------------------------
  * Per-voxel case index (_get_cubeindex, src/common.jl:10-20; corner order of the counted algo) for the
  * last counted field, (nx-1)(ny-1)(nz-1) bytes in scan-rank order ((x*(ny-1)+y)*(nz-1)+z). */

@@ -69,6 +69,8 @@ def load():
     L.b200iso_count_async.argtypes = [vp, pp, vp, i64, i64, i64, i64, vp]
     L.b200iso_generate_async.argtypes = [vp, vp, i64, vp, i64, vp, i64]
     L.b200iso_totals.argtypes = [vp, pi64, pi64, pci]
+    L.b200iso_extract_async.argtypes = [vp, pp, vp, i64, i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]
+    L.b200iso_add_vertex_base_async.argtypes = [vp, vp, i64, vp, vp]
     L.b200iso_case_indices.argtypes = [vp, vp, ci]
     L.b200iso_enable_timing.argtypes = [vp, ci]
     L.b200iso_timings.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ci]
@@ -126,6 +128,18 @@ class Handle:
     def generate_async(self, verts_dev_ptr, vcap, faces_dev_ptr, fcap, vertex_base_dev_ptr=0, vertex_base=0):
         _check(self.L.b200iso_generate_async(self.h, ctypes.c_void_p(verts_dev_ptr), vcap, ctypes.c_void_p(faces_dev_ptr), fcap,
                                              ctypes.c_void_p(vertex_base_dev_ptr or 0), vertex_base))
+
+    def extract_async(self, params, sdf_dev_ptr, nx, ny, nz, ldx, verts_dev_ptr, vcap, faces_dev_ptr, fcap,
+                      vertex_base_dev_ptr=0, vertex_base=0, totals_dev_ptr=0):
+        """classify + single-pass count/scan/generate, fully asynchronous (device buffers with capacity)."""
+        _check(self.L.b200iso_extract_async(self.h, ctypes.byref(params), ctypes.c_void_p(sdf_dev_ptr), nx, ny, nz, ldx,
+                                            ctypes.c_void_p(verts_dev_ptr), vcap, ctypes.c_void_p(faces_dev_ptr), fcap,
+                                            ctypes.c_void_p(vertex_base_dev_ptr or 0), vertex_base,
+                                            ctypes.c_void_p(totals_dev_ptr or 0)))
+
+    def add_vertex_base_async(self, faces_dev_ptr, fcap, totals_dev_ptr, vertex_base_dev_ptr):
+        _check(self.L.b200iso_add_vertex_base_async(self.h, ctypes.c_void_p(faces_dev_ptr), fcap,
+                                                    ctypes.c_void_p(totals_dev_ptr), ctypes.c_void_p(vertex_base_dev_ptr)))
 
     def totals(self):
         nv, nf, f64 = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()

@@ -87,6 +87,7 @@ struct b200iso_handle {
   b200iso_params prm{};
   iso::Grid grid{};
   const float* sdf_dev = nullptr;
+  long long* totals_out = nullptr;
   long long nblocks = 0;
   int vert_is_f64 = 0;
   long long nverts = 0, nfaces = 0;
@@ -135,8 +136,9 @@ int check_params(const b200iso_params* p, int64_t nx, int64_t ny, int64_t nz, in
   return 0;
 }
 
+// fused = true: classify + coordinates only; the caller enqueues the single-pass generate kernel next.
 int enqueue_count(b200iso_handle* h, const b200iso_params* p, const float* sdf_dev, int64_t nx, int64_t ny, int64_t nz,
-                  int64_t ldx, long long* totals_out, bool step_begun = false) {
+                  int64_t ldx, long long* totals_out, bool step_begun = false, bool fused = false) {
   cudaStream_t st = h->stream;
   h->prm = *p;
   h->sdf_dev = sdf_dev;
@@ -177,10 +179,12 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const float* sdf_d
     h->launches++;
   }
   if (int rc = h->rec(b200iso_handle::E_C1)) return rc;
-  // (2) count + decoupled look-back scan
+  // (2) count + decoupled look-back scan (in the fused form the generate kernel does this itself)
   CU(cudaMemsetAsync(h->status.p, 0, (size_t)h->nblocks * 2 * sizeof(unsigned long long), st));
   CU(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int), st));
-  if (p->algo == B200ISO_MC)
+  h->totals_out = totals_out;
+  if (fused) {
+  } else if (p->algo == B200ISO_MC)
     iso::count_kernel<0><<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->status.p, h->ticket, h->nblocks, h->totals_dev, totals_out, nullptr);
   else
     iso::count_kernel<1><<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->status.p, h->ticket, h->nblocks, h->totals_dev, totals_out, h->celloff.p);
@@ -201,7 +205,7 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const float* sdf_d
 }
 
 int enqueue_generate(b200iso_handle* h, void* verts_dev, int64_t vcap, int64_t* faces_dev, int64_t fcap,
-                     const int64_t* vertex_base_dev, int64_t vertex_base) {
+                     const int64_t* vertex_base_dev, int64_t vertex_base, bool fused = false) {
   if (!h->counted) return fail(B200ISO_ESTATE, "generate called before count");
   cudaStream_t st = h->stream;
   if (int rc = h->rec(b200iso_handle::E_G0)) return rc;
@@ -213,13 +217,19 @@ int enqueue_generate(b200iso_handle* h, void* verts_dev, int64_t vcap, int64_t* 
     a.vbase_dev = (const long long*)vertex_base_dev, a.vbase = vertex_base;
     a.iso_d = p.iso, a.iso_f = (float)p.iso, a.eps_d = p.eps, a.eps_f = (float)p.eps;
     a.iso_is_f32 = p.iso_is_f32, a.eps_is_f32 = p.eps_is_f32, a.p_is_f32 = p.range_kind == B200ISO_RANGE_F32;
+    a.ticket = h->ticket, a.nblocks = h->nblocks, a.totals_a = h->totals_dev, a.totals_b = h->totals_out;
     const unsigned nb = (unsigned)h->nblocks;
     const bool pf32 = p.range_kind == B200ISO_RANGE_F32;
-    if (p.algo == B200ISO_MC) {
-      if (!p.iso_is_f32) iso::mc_generate_kernel<2, double><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
-      else if (pf32) iso::mc_generate_kernel<1, float><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
-      else if (h->vert_is_f64) iso::mc_generate_kernel<0, double><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
-      else iso::mc_generate_kernel<0, float><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+    if (p.algo == B200ISO_MC && fused) {
+      if (!p.iso_is_f32) iso::mc_generate_kernel<2, double, true><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+      else if (pf32) iso::mc_generate_kernel<1, float, true><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+      else if (h->vert_is_f64) iso::mc_generate_kernel<0, double, true><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+      else iso::mc_generate_kernel<0, float, true><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+    } else if (p.algo == B200ISO_MC) {
+      if (!p.iso_is_f32) iso::mc_generate_kernel<2, double, false><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+      else if (pf32) iso::mc_generate_kernel<1, float, false><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+      else if (h->vert_is_f64) iso::mc_generate_kernel<0, double, false><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+      else iso::mc_generate_kernel<0, float, false><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
     } else {
       if (int rc = iso::launch_mt_generate(a, h->grid, p, h->vert_is_f64, h->celloff.p, nb, st)) return fail(B200ISO_EINVAL, "MT launch failed (%d)", rc);
     }
@@ -312,6 +322,33 @@ int b200iso_generate_async(b200iso_handle* h, void* verts_dev, int64_t vcap, int
   if ((vcap > 0 && !verts_dev) || (fcap > 0 && !faces_dev)) return fail(B200ISO_EINVAL, "output pointer is NULL");
   CU(cudaSetDevice(h->device));
   return enqueue_generate(h, verts_dev, vcap, faces_dev, fcap, vertex_base_dev, vertex_base);
+}
+
+int b200iso_extract_async(b200iso_handle* h, const b200iso_params* p, const float* sdf_dev, int64_t nx, int64_t ny, int64_t nz,
+                          int64_t ldx, void* verts_dev, int64_t vcap, int64_t* faces_dev, int64_t fcap,
+                          const int64_t* vertex_base_dev, int64_t vertex_base, int64_t* totals_dev) {
+  if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  if (int rc = check_params(p, nx, ny, nz, ldx)) return rc;
+  if (!sdf_dev && nx * ny * nz > 0) return fail(B200ISO_EINVAL, "sdf is NULL");
+  if (vcap < 0 || fcap < 0) return fail(B200ISO_EINVAL, "negative capacity");
+  if ((vcap > 0 && !verts_dev) || (fcap > 0 && !faces_dev)) return fail(B200ISO_EINVAL, "output pointer is NULL");
+  CU(cudaSetDevice(h->device));
+  const bool fused = p->algo == B200ISO_MC;
+  if (int rc = enqueue_count(h, p, sdf_dev, nx, ny, nz, ldx, (long long*)totals_dev, false, fused)) return rc;
+  return enqueue_generate(h, verts_dev, vcap, faces_dev, fcap, vertex_base_dev, vertex_base, fused);
+}
+
+int b200iso_add_vertex_base_async(b200iso_handle* h, int64_t* faces_dev, int64_t fcap, const int64_t* totals_dev,
+                                  const int64_t* vertex_base_dev) {
+  if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  if (!faces_dev || !totals_dev || !vertex_base_dev) return fail(B200ISO_EINVAL, "NULL argument");
+  if ((reinterpret_cast<uintptr_t>(faces_dev) & 15) != 0) return fail(B200ISO_EINVAL, "faces must be 16-byte aligned");
+  CU(cudaSetDevice(h->device));
+  iso::add_base_kernel<<<148 * 8, 256, 0, h->stream>>>((long long*)faces_dev, fcap, (const long long*)totals_dev,
+                                                       (const long long*)vertex_base_dev);
+  CU(cudaGetLastError());
+  h->launches++;
+  return 0;
 }
 
 int b200iso_totals(b200iso_handle* h, int64_t* nverts, int64_t* nfaces, int* vert_is_f64) {

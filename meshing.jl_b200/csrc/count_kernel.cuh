@@ -1,9 +1,9 @@
 // count_kernel.cuh -- (2) count + single-pass decoupled look-back scan.  ALGO 0 = MC, 1 = MT.
 //
-// Same block/thread mapping as generate (iso_kernels.cuh, thread_map): a block owns whole voxel columns,
-// lanes run across 32 adjacent columns, so empty regions are skipped per warp.  Blocks are numbered in the
-// reference's scan order (x, then y, then z) through an atomic ticket and publish their totals to the
-// look-back chain.
+// Used by the two-phase ABI (b200iso_count -> caller allocates -> b200iso_generate) and by MT; the
+// single-GPU MC fast path fuses this work into mc_generate_kernel<.., FUSED = true>.
+// Same block/thread mapping as generate (thread_map): one thread per quad-cell, thread order == scan order.
+// Blocks are numbered through an atomic ticket and publish their totals to the look-back chain.
 //   MC: vertices = crossed cube edges (12 masked popcounts per word), faces = table per active voxel
 //   MT: vertices = owned crossed edges (7+ masked popcounts per word), faces = table per active voxel;
 //       additionally writes celloff[cell] = vertices created in this block before the cell, which the
@@ -19,25 +19,26 @@ __global__ void __launch_bounds__(CB_THREADS)
 count_kernel(const uint32_t* __restrict__ bits, Grid g, unsigned long long* status, unsigned int* ticket,
              long long nblocks, long long* totals_a, long long* totals_b, uint32_t* __restrict__ celloff) {
   __shared__ uint8_t nf_s[256];
-  __shared__ uint32_t s_val[CB_THREADS], s_w[CB_THREADS / 32];
+  __shared__ uint32_t s_w[CB_THREADS / 32];
   __shared__ uint32_t red_v[CB_THREADS / 32], red_f[CB_THREADS / 32];
-  __shared__ long long sb;
+  __shared__ unsigned sb;
   if (threadIdx.x == 0) sb = atomicAdd(ticket, 1u);
-  nf_s[threadIdx.x] = ALGO == 0 ? (uint8_t)((ISO_MC_VERTS[threadIdx.x] >> 52) & 7) : ISO_MT_NF[threadIdx.x];
+  for (int i = threadIdx.x; i < 256; i += CB_THREADS) nf_s[i] = ALGO == 0 ? (uint8_t)((ISO_MC_VERTS[i] >> 52) & 7) : ISO_MT_NF[i];
   __syncthreads();
-  const long long b = sb;
+  const unsigned b = sb;
   const TMap tm = thread_map(g, b);
-  const int fxy = (tm.x == 0 ? 1 : 0) | (tm.y == 0 ? 2 : 0);
   uint32_t nv = 0, nf = 0;
+  uint32_t cv[4] = {0, 0, 0, 0};
   if (tm.live) {
-    for (int zq = tm.zq_lo; zq < tm.zq_hi; ++zq) {
-      Quad q;
-      if (!load_quad(bits, g, tm.x, tm.y, zq, q)) continue;
+    Quad q;
+    if (load_quad(bits, g, tm.x, tm.y, tm.zq, q)) {
+      const int fxy = (tm.x == 0 ? 1 : 0) | (tm.y == 0 ? 2 : 0);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint32_t mm = active_mask(q, i);
         if (mm) {
-          nv += ALGO == 0 ? mc_nverts_masked(q, i, q.vm[i]) : mt_owned_masked(q, i, q.vm[i], fxy, zq == 0 && i == 0);
+          cv[i] = ALGO == 0 ? mc_nverts_masked(q, i, q.vm[i]) : mt_owned_masked(q, i, q.vm[i], fxy, tm.zq == 0 && i == 0);
+          nv += cv[i];
           while (mm) {
             const int k = __ffs(mm) - 1;
             mm &= mm - 1;
@@ -48,23 +49,13 @@ count_kernel(const uint32_t* __restrict__ bits, Grid g, unsigned long long* stat
     }
   }
   if (ALGO == 1) {
-    // in-block exclusive vertex prefix of every cell, in scan order (a thread's cells are consecutive)
+    // in-block exclusive vertex prefix of every cell (thread order == scan order)
     uint32_t tot;
-    uint32_t run = block_excl_scan_ord(nv, tm.ord, s_val, s_w, tot);
+    const uint32_t e0 = block_excl_scan_u32(nv, s_w, tot);
     if (tm.live) {
-      for (int zq = tm.zq_lo; zq < tm.zq_hi; ++zq) {
-        Quad q;
-        uint32_t cv[4] = {0, 0, 0, 0};
-        if (load_quad(bits, g, tm.x, tm.y, zq, q)) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (active_mask(q, i)) cv[i] = mt_owned_masked(q, i, q.vm[i], fxy, zq == 0 && i == 0);
-        }
-        uint4 o;
-        o.x = run, o.y = run + cv[0], o.z = o.y + cv[1], o.w = o.z + cv[2];
-        run = o.w + cv[3];
-        *reinterpret_cast<uint4*>(celloff + (long long)tm.x * g.row_words + (long long)tm.y * g.W + zq * 4) = o;
-      }
+      uint4 o;
+      o.x = e0, o.y = e0 + cv[0], o.z = o.y + cv[1], o.w = o.z + cv[2];
+      *reinterpret_cast<uint4*>(celloff + (long long)tm.x * g.row_words + (long long)tm.y * g.W + tm.zq * 4) = o;
     }
   }
   // block totals
@@ -80,8 +71,8 @@ count_kernel(const uint32_t* __restrict__ bits, Grid g, unsigned long long* stat
 #pragma unroll
     for (int w = 0; w < CB_THREADS / 32; ++w) av += red_v[w], af += red_f[w];
     unsigned long long ev, ef;
-    lookback(status, b, av, af, ev, ef);
-    if (b == nblocks - 1 && threadIdx.x == 0) {
+    lookback(status, (long long)b, av, af, ev, ef);
+    if ((long long)b == nblocks - 1 && threadIdx.x == 0) {
       totals_a[0] = (long long)(ev + av), totals_a[1] = (long long)(ef + af);
       if (totals_b) totals_b[0] = (long long)(ev + av), totals_b[1] = (long long)(ef + af);
     }

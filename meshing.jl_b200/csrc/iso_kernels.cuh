@@ -31,26 +31,21 @@ namespace iso {
 // problem geometry and the block/thread -> voxel mapping shared by count / generate
 //
 // Unit of work: the quad-cell = 4 consecutive z-words = 128 z-consecutive voxels of one voxel column (x,y).
-// A block owns whole columns (so its voxels are one contiguous range of the reference's scan order):
-// CGB groups of 32 adjacent columns of one x-row.  LANES RUN ACROSS COLUMNS (y), warps across z: the 32
-// lanes of a warp look at the same z-range of 32 neighbouring columns, which the surface crosses either
-// in most of them or in none -- so a warp can skip an empty region with one vote, and the per-voxel loops
-// of its lanes have similar trip counts.
+// The quad-cells of one voxel x-row, ordered (y, z), are in the reference's scan order; thread t of a block
+// takes quad-cell (first of the block) + t, so a block owns one contiguous range of the output order,
+// thread order == scan order, and the 16-byte loads of consecutive lanes are contiguous in memory.
 struct Grid {
   int nx, ny, nz;        // samples
   int W;                 // words per sample column (multiple of 4, >= ceil(nz/32))
   int Wq;                // W / 4 : quad-cells per column
-  int WZ;                // warps along z per column group: min(Wq, 8)
-  int QPT;               // quad-cells per thread: ceil(Wq / WZ) (consecutive in z)
-  int CGB;               // 32-column groups per block: 8 / WZ
-  int cols_per_block;    // 32 * CGB
-  int blocks_per_row;    // ceil((ny-1) / cols_per_block)
+  int quads_per_row;     // (ny-1) * Wq : quad-cells of one voxel x-row, in scan order (y, z)
+  int blocks_per_row;    // ceil(quads_per_row / CB_THREADS)
   long long row_words;   // ny * W : words between sample column (x,y) and (x+1,y)
   long long ldx;         // field leading dimension (elements)
   long long plane;       // ldx * ny
 };
 
-constexpr int CB_THREADS = 256;  // threads per count/generate block (8 warps)
+constexpr int CB_THREADS = 128;  // threads (= quad-cells) per count/generate block
 
 inline void grid_setup(Grid& g, long long nx, long long ny, long long nz, long long ldx) {
   g.nx = (int)nx, g.ny = (int)ny, g.nz = (int)nz;
@@ -59,34 +54,24 @@ inline void grid_setup(Grid& g, long long nx, long long ny, long long nz, long l
   g.W = (words + 3) / 4 * 4;
   if (g.W == 0) g.W = 4;
   g.Wq = g.W / 4;
-  g.WZ = g.Wq < 8 ? g.Wq : 8;
-  g.QPT = (g.Wq + g.WZ - 1) / g.WZ;
-  g.CGB = 8 / g.WZ;
-  g.cols_per_block = 32 * g.CGB;
   g.row_words = ny * g.W;
-  g.blocks_per_row = (int)(((ny > 0 ? ny - 1 : 0) + g.cols_per_block - 1) / g.cols_per_block);
+  g.quads_per_row = (int)((ny > 0 ? ny - 1 : 0) * g.Wq);
+  g.blocks_per_row = (g.quads_per_row + CB_THREADS - 1) / CB_THREADS;
 }
 
 // what one thread of block b works on
 struct TMap {
-  int x, y;          // voxel column
-  int zq_lo, zq_hi;  // its quad-cells [zq_lo, zq_hi)
-  int ord;           // position of the thread in the block's scan order (column-major, z-minor), 0..255
+  int x, y, zq;  // quad-cell zq of voxel column (x, y)
   bool live;
 };
 
-__device__ __forceinline__ TMap thread_map(const Grid& g, long long b) {
+__device__ __forceinline__ TMap thread_map(const Grid& g, unsigned b) {
   TMap m;
-  m.x = (int)(b / g.blocks_per_row);
-  const int cb = (int)(b - (long long)m.x * g.blocks_per_row);
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cg = w / g.WZ, wz = w - cg * g.WZ;
-  m.y = cb * g.cols_per_block + cg * 32 + lane;
-  m.zq_lo = wz * g.QPT;
-  m.zq_hi = min(g.Wq, m.zq_lo + g.QPT);
-  m.live = cg < g.CGB && m.y < g.ny - 1 && m.zq_lo < m.zq_hi;
-  const int used = g.CGB * g.WZ * 32;  // threads that own a slot of the scan order
-  m.ord = cg < g.CGB ? (cg * 32 + lane) * g.WZ + wz : used + ((int)threadIdx.x - used);
+  m.x = (int)(b / (unsigned)g.blocks_per_row);
+  const int qr = (int)(b - (unsigned)m.x * (unsigned)g.blocks_per_row) * CB_THREADS + (int)threadIdx.x;
+  m.y = qr / g.Wq;
+  m.zq = qr - m.y * g.Wq;
+  m.live = qr < g.quads_per_row;
   return m;
 }
 
@@ -233,11 +218,12 @@ __device__ __forceinline__ bool load_quad(const uint32_t* __restrict__ bits, con
   const uint32_t n10 = more ? __ldg(c10 + 4) : 0u, n11 = more ? __ldg(c10 + g.W + 4) : 0u;
   // bits of samples beyond nz are 0, so an all-ones run that reaches the padding reads as "mixed" here;
   // that only costs the slow path, the exact valid-mask is applied below.
-  const uint32_t nb = (n00 & n01 & n10 & n11 & 1u) ? 0xffffffffu : ((n00 | n01 | n10 | n11) & 1u ? 0x1u : 0u);
+  const uint32_t nany = (n00 | n01 | n10 | n11) & 1u;
+  const uint32_t nall = more ? ((n00 & n01 & n10 & n11 & 1u) ? 0xffffffffu : 0u) : 0xffffffffu;
   const uint32_t any = a00.x | a00.y | a00.z | a00.w | a01.x | a01.y | a01.z | a01.w | a10.x | a10.y | a10.z | a10.w |
-                       a11.x | a11.y | a11.z | a11.w | (nb & 1u);
+                       a11.x | a11.y | a11.z | a11.w | nany;
   const uint32_t all = a00.x & a00.y & a00.z & a00.w & a01.x & a01.y & a01.z & a01.w & a10.x & a10.y & a10.z & a10.w &
-                       a11.x & a11.y & a11.z & a11.w & (more ? nb : 0xffffffffu);
+                       a11.x & a11.y & a11.z & a11.w & nall;
   if (any == 0u || all == 0xffffffffu) return false;
   shift_up(a00, n00, q.s00, q.t00);
   shift_up(a01, n01, q.s01, q.t01);
@@ -280,6 +266,7 @@ __device__ __forceinline__ uint32_t mc_nverts_masked(const Quad& q, int i, uint3
   return n;
 }
 
+
 // ---- block scans (256 threads) ---------------------------------------------------------------------------
 // exclusive scan in thread order; s_w: 8 words of shared scratch.  Contains two barriers.
 __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* s_w, uint32_t& total) {
@@ -304,16 +291,6 @@ __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* s_
   return base + inc - v;
 }
 
-// exclusive scan in the block's SCAN ORDER (TMap::ord): values are transposed through s_val[256]
-__device__ __forceinline__ uint32_t block_excl_scan_ord(uint32_t v, int ord, uint32_t* s_val, uint32_t* s_w, uint32_t& total) {
-  s_val[ord] = v;
-  __syncthreads();
-  const uint32_t u = s_val[threadIdx.x];
-  const uint32_t e = block_excl_scan_u32(u, s_w, total);
-  s_val[threadIdx.x] = e;
-  __syncthreads();
-  return s_val[ord];
-}
 
 // ------------------------------------------------------------------------------------------------------
 // decoupled look-back scan state: one 16-byte entry per block, {nverts, nfaces}, each word
@@ -443,6 +420,11 @@ struct GenArgs {
   float eps_f;
   double eps_d;
   int iso_is_f32, eps_is_f32, p_is_f32;  // typeof(iso), typeof(eps), eltype of the points (ranges)
+  // fused single-pass kernels only: ticket counter, number of blocks, where the last block writes the totals
+  unsigned int* ticket;
+  long long nblocks;
+  long long* totals_a;
+  long long* totals_b;
 };
 
 template <int MODE>
@@ -471,7 +453,6 @@ __device__ __forceinline__ void mc_interp(const GenArgs& a, float va, float vb, 
     }
   }
 }
-
 constexpr int GEN_NB = CB_THREADS;     // active voxels per dense round (one per thread)
 constexpr int GEN_MAXV = GEN_NB * 12;  // vertices of a round (MC: <= 12 per voxel)
 constexpr int GEN_MAXF = GEN_NB * 5;   // faces of a round (MC: <= 5 per voxel)
@@ -481,73 +462,139 @@ constexpr int GEN_MAXF = GEN_NB * 5;   // faces of a round (MC: <= 5 per voxel)
 template <int ALGO>
 __device__ __forceinline__ void push_records(const uint32_t* __restrict__ bits, const Grid& g, const TMap& tm, uint32_t a0,
                                              uint32_t lo, uint32_t hi, uint32_t* rec_yz, uint8_t* rec_c) {
+  Quad q;
+  if (!load_quad(bits, g, tm.x, tm.y, tm.zq, q)) return;
   uint32_t idx = a0;
-  for (int zq = tm.zq_lo; zq < tm.zq_hi && idx < hi; ++zq) {
-    Quad q;
-    if (!load_quad(bits, g, tm.x, tm.y, zq, q)) continue;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint32_t mm = active_mask(q, i);
-      if (idx + __popc(mm) <= lo) {  // whole cell before the window
-        idx += __popc(mm);
-        continue;
+  for (int i = 0; i < 4; ++i) {
+    uint32_t mm = active_mask(q, i);
+    if (idx + __popc(mm) <= lo || idx >= hi) {  // whole cell outside the window
+      idx += __popc(mm);
+      continue;
+    }
+    while (mm) {
+      const int k = __ffs(mm) - 1;
+      mm &= mm - 1;
+      if (idx >= lo && idx < hi) {
+        const uint32_t s = idx - lo;
+        rec_yz[s] = (uint32_t)tm.y | ((uint32_t)((tm.zq * 4 + i) * 32 + k) << 16);
+        rec_c[s] = (uint8_t)case_of<ALGO>(q, i, k);
       }
-      while (mm) {
-        const int k = __ffs(mm) - 1;
-        mm &= mm - 1;
-        if (idx >= lo && idx < hi) {
-          const uint32_t s = idx - lo;
-          rec_yz[s] = (uint32_t)tm.y | ((uint32_t)((zq * 4 + i) * 32 + k) << 16);
-          rec_c[s] = (uint8_t)case_of<ALGO>(q, i, k);
-        }
-        ++idx;
-      }
+      ++idx;
     }
   }
 }
 
-// number of active voxels of this thread's quad-cells
+// number of active voxels of this thread's quad-cell
 __device__ __forceinline__ uint32_t count_active(const uint32_t* __restrict__ bits, const Grid& g, const TMap& tm) {
   uint32_t na = 0;
-  if (tm.live)
-    for (int zq = tm.zq_lo; zq < tm.zq_hi; ++zq) {
-      Quad q;
-      if (!load_quad(bits, g, tm.x, tm.y, zq, q)) continue;
+  if (tm.live) {
+    Quad q;
+    if (load_quad(bits, g, tm.x, tm.y, tm.zq, q)) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) na += __popc(active_mask(q, i));
     }
+  }
   return na;
 }
 
-template <int MODE, typename V>
-__global__ void __launch_bounds__(CB_THREADS, 4)
+// Block id: FUSED kernels take a ticket (blocks must be numbered in an order in which every predecessor
+// has already started, for the look-back chain); the others use blockIdx.
+template <bool FUSED>
+__device__ __forceinline__ unsigned block_id(unsigned int* ticket, unsigned* s_b) {
+  if (!FUSED) return blockIdx.x;
+  if (threadIdx.x == 0) *s_b = atomicAdd(ticket, 1u);
+  __syncthreads();
+  return *s_b;
+}
+
+// Exclusive prefixes (vertices, faces) of block b in the whole mesh.
+//   !FUSED: count_kernel ran before and left the inclusive prefixes in `status`.
+//    FUSED: this block publishes its own totals and looks back (warp 0), everyone else waits at the barrier.
+template <bool FUSED>
+__device__ __forceinline__ void block_base(const GenArgs& a, unsigned b, unsigned long long tot_v, unsigned long long tot_f,
+                                           unsigned long long* s_base, unsigned long long& bv, unsigned long long& bf) {
+  if (!FUSED) {
+    bv = bf = 0;
+    if (b > 0) {
+      bv = a.status[2 * (unsigned long long)(b - 1)] & VAL_MASK;
+      bf = a.status[2 * (unsigned long long)(b - 1) + 1] & VAL_MASK;
+    }
+    return;
+  }
+  if (threadIdx.x < 32) {
+    unsigned long long ev, ef;
+    lookback(const_cast<unsigned long long*>(a.status), (long long)b, tot_v, tot_f, ev, ef);
+    if (threadIdx.x == 0) {
+      s_base[0] = ev, s_base[1] = ef;
+      if ((long long)b == a.nblocks - 1) {
+        a.totals_a[0] = (long long)(ev + tot_v), a.totals_a[1] = (long long)(ef + tot_f);
+        if (a.totals_b) a.totals_b[0] = (long long)(ev + tot_v), a.totals_b[1] = (long long)(ef + tot_f);
+      }
+    }
+  }
+  __syncthreads();
+  bv = s_base[0], bf = s_base[1];
+}
+
+// FUSED = false: generate after count_kernel (two-phase ABI: the caller sizes its arrays in between).
+// FUSED = true : classify-output -> mesh in ONE pass: count, decoupled look-back scan and generate fused
+//                (outputs must have capacity; totals are written by the last block).
+template <int MODE, typename V, bool FUSED>
+__global__ void __launch_bounds__(CB_THREADS, 1024 / CB_THREADS)
 mc_generate_kernel(GenArgs a, Grid g) {
   __shared__ unsigned long long tabV[256], tabF[256];
-  __shared__ uint32_t s_val[CB_THREADS], s_w[CB_THREADS / 32];
+  __shared__ unsigned long long s_base[2];
+  __shared__ uint32_t s_w[CB_THREADS / 32];
+  __shared__ unsigned s_b;
   __shared__ uint32_t rec_yz[GEN_NB];
   __shared__ uint16_t rec_v[GEN_NB], rec_f[GEN_NB];
   __shared__ uint8_t rec_c[GEN_NB];
-  __shared__ float corner[GEN_NB][8];
+  __shared__ __align__(16) float corner[GEN_NB][8];
   __shared__ uint8_t owner_v[GEN_MAXV], owner_f[GEN_MAXF];
   __shared__ uint8_t edge_c[12];
 
   const int tid = threadIdx.x;
-  const long long b = blockIdx.x;
+  const unsigned b = block_id<FUSED>(a.ticket, &s_b);
   const TMap tm = thread_map(g, b);
-  // ---- A: active voxels per thread, exclusive scan in scan order ----
+  // ---- A: active voxels per thread, exclusive scan (thread order == scan order) ----
   const uint32_t tna = count_active(a.bits, g, tm);
   uint32_t blk_na;
-  const uint32_t my_a0 = block_excl_scan_ord(tna, tm.ord, s_val, s_w, blk_na);
-  if (blk_na == 0) return;  // uniform: nothing crosses this block
-
-  tabV[tid] = ISO_MC_VERTS[tid];
-  tabF[tid] = ISO_MC_FACES[tid];
+  const uint32_t my_a0 = block_excl_scan_u32(tna, s_w, blk_na);
+  if (blk_na == 0) {  // uniform: nothing crosses this block
+    if (FUSED) {
+      unsigned long long bv, bf;
+      block_base<true>(a, b, 0, 0, s_base, bv, bf);
+    }
+    return;
+  }
+  for (int i = tid; i < 256; i += CB_THREADS) tabV[i] = ISO_MC_VERTS[i], tabF[i] = ISO_MC_FACES[i];
   if (tid < 12) edge_c[tid] = ISO_MC_EDGE_CORNERS[tid];
-  // exclusive prefixes of this block in the whole mesh (published by count_kernel)
+
   unsigned long long bv = 0, bf = 0;
-  if (b > 0) {
-    bv = a.status[2 * (b - 1)] & VAL_MASK;
-    bf = a.status[2 * (b - 1) + 1] & VAL_MASK;
+  bool have_base = false;
+  if (!FUSED) {
+    block_base<false>(a, b, 0, 0, s_base, bv, bf);
+    have_base = true;
+  } else if (blk_na > (uint32_t)GEN_NB) {
+    // several windows: the block totals are needed before anything can be emitted -> counting pre-pass
+    __syncthreads();  // tables
+    uint32_t tv = 0, tf = 0;
+    for (uint32_t lo = 0; lo < blk_na; lo += GEN_NB) {
+      const uint32_t hi = min(lo + (uint32_t)GEN_NB, blk_na);
+      if (tna && my_a0 < hi && my_a0 + tna > lo) push_records<0>(a.bits, g, tm, my_a0, lo, hi, rec_yz, rec_c);
+      __syncthreads();
+      if ((uint32_t)tid < hi - lo) {
+        const unsigned long long t = tabV[rec_c[tid]];
+        tv += (uint32_t)((t >> 48) & 15), tf += (uint32_t)((t >> 52) & 7);
+      }
+      __syncthreads();
+    }
+    uint32_t totv, totf;  // (block totals can exceed 16 bits per field: reduce the two fields separately)
+    block_excl_scan_u32(tv, s_w, totv);
+    block_excl_scan_u32(tf, s_w, totf);
+    block_base<true>(a, b, totv, totf, s_base, bv, bf);
+    have_base = true;
   }
   const long long vbase = a.vbase + (a.vbase_dev ? *a.vbase_dev : 0);
   const double* yp = a.coords + g.nx;
@@ -583,8 +630,13 @@ mc_generate_kernel(GenArgs a, Grid g) {
       for (uint32_t i = 0; i < nv; ++i) owner_v[v0 + i] = (uint8_t)tid;
       for (uint32_t i = 0; i < nf; ++i) owner_f[f0 + i] = (uint8_t)tid;
     }
-    __syncthreads();
     const uint32_t nvr = wtot & 0xffffu, nfr = wtot >> 16;
+    if (FUSED && !have_base) {  // single window: its totals are the block totals
+      block_base<true>(a, b, nvr, nfr, s_base, bv, bf);
+      have_base = true;
+    } else {
+      __syncthreads();
+    }
 
     // ---- B2: thread per vertex (vertex_interp, src/marching_cubes.jl:100-104) ----
     for (uint32_t k = tid; k < nvr; k += CB_THREADS) {
@@ -624,6 +676,22 @@ mc_generate_kernel(GenArgs a, Grid g) {
     bv += nvr, bf += nfr;  // next window continues where this one ended
     __syncthreads();
   }
+}
+
+// faces[0 .. 3*min(totals[1], fcap)) += *base   (sharded fix-up after the all-gather of the slab totals)
+__global__ void add_base_kernel(long long* __restrict__ faces, long long fcap, const long long* __restrict__ totals,
+                                const long long* __restrict__ base) {
+  const long long add = *base;
+  const long long nf = totals[1] < fcap ? totals[1] : fcap;
+  const long long n2 = nf * 3 / 2;  // pairs of indices
+  if (add == 0) return;
+  longlong2* f2 = reinterpret_cast<longlong2*>(faces);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    longlong2 v = f2[i];
+    v.x += add, v.y += add;
+    f2[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && ((nf * 3) & 1)) faces[nf * 3 - 1] += add;
 }
 
 }  // namespace iso

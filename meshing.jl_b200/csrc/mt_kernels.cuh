@@ -102,7 +102,7 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
   __shared__ uint8_t nown0_s[256], nf_s[256];
   __shared__ uint16_t einfo_s[20];
   __shared__ uint8_t eshift_s[160];
-  __shared__ uint32_t s_val[CB_THREADS], s_w[CB_THREADS / 32];
+  __shared__ uint32_t s_w[CB_THREADS / 32];
   __shared__ uint32_t rec_yz[MTG_NB], rec_vc[MTG_NB], rec_f[MTG_NB];
   __shared__ uint8_t rec_c[MTG_NB];
   __shared__ int32_t evid[MTG_NB * MTG_EDGES];  // vertex id of each crossed edge, relative to the block's first vertex
@@ -110,27 +110,29 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
   __shared__ uint8_t owner_f[MTG_MAXF];
 
   const int tid = threadIdx.x;
-  own0_s[tid] = ISO_MT_OWNED[tid * 8];
-  nown0_s[tid] = ISO_MT_NOWN[tid * 8];
-  nf_s[tid] = ISO_MT_NF[tid];
-  cross_s[tid] = ISO_MT_CROSS[tid];
+  for (int i = tid; i < 256; i += CB_THREADS) {
+    own0_s[i] = ISO_MT_OWNED[i * 8];
+    nown0_s[i] = ISO_MT_NOWN[i * 8];
+    nf_s[i] = ISO_MT_NF[i];
+    cross_s[i] = ISO_MT_CROSS[i];
+  }
   for (int i = tid; i < 768; i += CB_THREADS) faces_s[i] = ISO_MT_FACES[i];
-  if (tid < 20) einfo_s[tid] = ISO_MT_EDGE_INFO[tid];
-  if (tid < 160) eshift_s[tid] = ISO_MT_EDGE_SHIFT[tid];
+  for (int i = tid; i < 20; i += CB_THREADS) einfo_s[i] = ISO_MT_EDGE_INFO[i];
+  for (int i = tid; i < 160; i += CB_THREADS) eshift_s[i] = ISO_MT_EDGE_SHIFT[i];
 
-  const long long b = blockIdx.x;
+  const unsigned b = blockIdx.x;
   const TMap tm = thread_map(g, b);
   const int x = tm.x;
-  // ---- A: active voxels per thread, exclusive scan in scan order ----
+  // ---- A: active voxels per thread, exclusive scan (thread order == scan order) ----
   const uint32_t tna = count_active(a.bits, g, tm);
   uint32_t blk_na;
-  const uint32_t my_a0 = block_excl_scan_ord(tna, tm.ord, s_val, s_w, blk_na);
+  const uint32_t my_a0 = block_excl_scan_u32(tna, s_w, blk_na);
   if (blk_na == 0) return;
 
   unsigned long long bv = 0, bf = 0;
   if (b > 0) {
-    bv = a.status[2 * (b - 1)] & VAL_MASK;
-    bf = a.status[2 * (b - 1) + 1] & VAL_MASK;
+    bv = a.status[2 * (unsigned long long)(b - 1)] & VAL_MASK;
+    bf = a.status[2 * (unsigned long long)(b - 1) + 1] & VAL_MASK;
   }
   const long long vbase = a.vbase + (a.vbase_dev ? *a.vbase_dev : 0);
   const double* xp = a.coords;
@@ -203,7 +205,7 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
         // vertices created before the owner voxel: block prefix + cell prefix + in-cell prefix
         const uint32_t below = q.vm[0] & ((1u << k) - 1u);
         const uint32_t incell = mt_owned_masked(q, 0, below, oflags & 3, (oz >> 5) == 0);
-        const long long ob = (long long)ox * g.blocks_per_row + oy / g.cols_per_block;  // the owner's block
+        const long long ob = (long long)ox * g.blocks_per_row + (oy * g.Wq + (oz >> 7)) / CB_THREADS;  // the owner's block
         const unsigned long long obv = ob > 0 ? (a.status[2 * (ob - 1)] & VAL_MASK) : 0ull;
         const uint32_t co = __ldg(celloff + (long long)ox * g.row_words + (long long)oy * g.W + (oz >> 5));
         id = (int32_t)((long long)(obv + co + incell + r) - (long long)bv);

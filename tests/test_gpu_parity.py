@@ -249,3 +249,65 @@ def test_sharded_slabs_equal_unsharded(pkg, oracle, world):
         parts.append(pkg.api.isosurface_slab(s[xa:xb], m, xa, shape[0], vb, X, Y, Z))
     v, f = pkg.sharding.stitch(parts)
     assert np.array_equal(f, f1) and _bits_equal(v, v1)
+
+
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+@pytest.mark.parametrize("shape", [(9, 40, 1100), (6, 70, 2200), (4, 5, 6000)])
+def test_tall_grids(pkg, oracle, algo, shape):
+    """nz > 1024: several quad-cells per thread; nz = 6000: bit-field too tall to stage in shared memory."""
+    _check(pkg, oracle, pkg.synth.gyroid(shape), algo)
+    _check(pkg, oracle, pkg.synth.noise(shape, seed=9), algo, iso=0.9)
+
+
+@pytest.mark.parametrize("shape,kind", [((48, 40, 56), "gyroid"), ((33, 21, 300), "noise"), ((20, 130, 37), "sphere"), ((3, 3, 3), "noise")])
+def test_fused_single_pass_extract(pkg, oracle, shape, kind):
+    """b200iso_extract_async: classify + ONE count/scan/generate kernel (decoupled look-back inside generate)."""
+    import torch
+    s = getattr(pkg.synth, kind)(shape)
+    vo, fo = oracle.isosurface(s, 0, iso_is_f32=True)
+    nx, ny, nz = shape
+    t = torch.from_numpy(np.ascontiguousarray(s.transpose(2, 1, 0))).cuda().permute(2, 1, 0)
+    h = pkg.capi.Handle(0)
+    p = pkg.api.make_params(pkg.MarchingCubes(iso=pkg.Float32(0)))
+    totals = torch.zeros(2, dtype=torch.int64, device="cuda")
+    verts = torch.full((len(vo) + 3, 3), -7.0, dtype=torch.float32, device="cuda")
+    faces = torch.full((len(fo) + 3, 3), -7, dtype=torch.int64, device="cuda")
+    h.set_stream(torch.cuda.current_stream().cuda_stream)
+    for _ in range(2):  # twice: the scan state must be reset between calls
+        h.extract_async(p, t.data_ptr(), nx, ny, nz, nx, verts.data_ptr(), verts.shape[0], faces.data_ptr(), faces.shape[0], 0, 0,
+                        totals.data_ptr())
+    torch.cuda.synchronize()
+    assert totals.tolist() == [len(vo), len(fo)] and h.totals()[:2] == (len(vo), len(fo))
+    assert _bits_equal(verts[: len(vo)].cpu().numpy(), vo) and (verts[len(vo):] == -7).all()
+    assert np.array_equal(faces[: len(fo)].cpu().numpy(), fo) and (faces[len(fo):] == -7).all()
+    # too-small buffers: totals are still exact, nothing is written past the capacity
+    if len(fo) > 4:
+        small = torch.full((len(fo) - 4, 3), -7, dtype=torch.int64, device="cuda")
+        h.extract_async(p, t.data_ptr(), nx, ny, nz, nx, verts.data_ptr(), 2, small.data_ptr(), small.shape[0], 0, 0, totals.data_ptr())
+        torch.cuda.synchronize()
+        assert totals.tolist() == [len(vo), len(fo)]
+        assert np.array_equal(small.cpu().numpy(), fo[: len(fo) - 4])
+    # sharded fix-up: faces += base on the device
+    base = torch.tensor([4321], dtype=torch.int64, device="cuda")
+    h.extract_async(p, t.data_ptr(), nx, ny, nz, nx, verts.data_ptr(), verts.shape[0], faces.data_ptr(), faces.shape[0], 0, 0, totals.data_ptr())
+    h.add_vertex_base_async(faces.data_ptr(), faces.shape[0], totals.data_ptr(), base.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(faces[: len(fo)].cpu().numpy(), fo + 4321) and (faces[len(fo):] == -7).all()
+    h.close()
+
+
+def test_fused_extract_mt_falls_back_to_two_kernels(pkg, oracle):
+    import torch
+    s = pkg.synth.gyroid((30, 31, 64))
+    vo, fo = oracle.isosurface(s, 1, iso_is_f32=True, eps_is_f32=True)
+    t = torch.from_numpy(np.ascontiguousarray(s.transpose(2, 1, 0))).cuda().permute(2, 1, 0)
+    h = pkg.capi.Handle(0)
+    p = pkg.api.make_params(pkg.MarchingTetrahedra(iso=pkg.Float32(0), eps=pkg.Float32(1e-3)))
+    verts = torch.empty((len(vo), 3), dtype=torch.float32, device="cuda")
+    faces = torch.empty((len(fo), 3), dtype=torch.int64, device="cuda")
+    h.set_stream(torch.cuda.current_stream().cuda_stream)
+    h.extract_async(p, t.data_ptr(), 30, 31, 64, 30, verts.data_ptr(), len(vo), faces.data_ptr(), len(fo))
+    torch.cuda.synchronize()
+    assert h.totals()[:2] == (len(vo), len(fo))
+    assert _bits_equal(verts.cpu().numpy(), vo) and np.array_equal(faces.cpu().numpy(), fo)
+    h.close()

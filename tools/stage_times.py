@@ -6,7 +6,8 @@ import numpy as np, torch
 from __graft_entry__ import load_package
 pkg = load_package()
 algo = sys.argv[1] if len(sys.argv) > 1 else "MC"
-sizes = [int(a) for a in sys.argv[2:]] or [256, 512, 1024]
+fused = "fused" in sys.argv
+sizes = [int(a) for a in sys.argv[2:] if a.isdigit()] or [256, 512, 1024]
 h = pkg.capi.Handle(0)
 h.enable_timing(True)
 for n in sizes:
@@ -17,13 +18,16 @@ for n in sizes:
     for it in range(8):
         if it == 3:
             h.enable_timing(True)  # resets the ring: average over the last 5 iterations only
-        nv, nf, f64 = h.count(p, t.data_ptr(), pkg.capi.DEVICE, n, n, n, t.stride(1))
-        verts = torch.empty((nv, 3), dtype=torch.float32, device="cuda")
-        faces = torch.empty((nf, 3), dtype=torch.int64, device="cuda")
-        h.generate(verts.data_ptr(), faces.data_ptr(), pkg.capi.DEVICE, 0)
+        if fused and it > 0:
+            h.extract_async(p, t.data_ptr(), n, n, n, t.stride(1), verts.data_ptr(), nv, faces.data_ptr(), nf)
+        else:
+            nv, nf, f64 = h.count(p, t.data_ptr(), pkg.capi.DEVICE, n, n, n, t.stride(1))
+            verts = torch.empty((nv, 3), dtype=torch.float32, device="cuda")
+            faces = torch.empty((nf, 3), dtype=torch.int64, device="cuda")
+            h.generate(verts.data_ptr(), faces.data_ptr(), pkg.capi.DEVICE, 0)
         tm = h.timings()
     tot = tm["classify_ms"] + tm["count_scan_ms"] + tm["generate_ms"]
     B = 4 * n ** 3 + 12 * nv + 24 * nf
-    print(f"{algo} n={n} nv={nv} nf={nf} classify={tm['classify_ms']:.3f} count={tm['count_scan_ms']:.3f} gen={tm['generate_ms']:.3f} "
+    print(f"{algo}{" fused" if fused else ""} n={n} nv={nv} nf={nf} classify={tm['classify_ms']:.3f} count={tm['count_scan_ms']:.3f} gen={tm['generate_ms']:.3f} "
           f"total={tot:.3f} ms  {(n-1)**3/tot/1e6:.1f} Gvox/s  {B/tot/1e6:.0f} GB/s  classify {4*n**3/tm['classify_ms']/1e6:.0f} GB/s", flush=True)
     del t, verts, faces
