@@ -1,0 +1,123 @@
+# B200Meshing.jl -- Julia host shim: the reference's `isosurface` signature on top of libb200iso.so.
+#
+# Drop-in for the two hot methods of Meshing.jl v0.7.0
+#     isosurface(sdf::AbstractArray{T,3}, method::MarchingCubes,      X=-1:1, Y=-1:1, Z=-1:1)   src/marching_cubes.jl:27
+#     isosurface(sdf::AbstractArray{T,3}, method::MarchingTetrahedra, X=-1:1, Y=-1:1, Z=-1:1)   src/marching_tetrahedra.jl:129
+# and the default forwarder isosurface(A, args...) (src/isosurface.jl:30-32), with the same exported names
+# (src/Meshing.jl:9-11), the same @kwdef method structs (src/algorithmtypes.jl:23-40), the same return types
+# (Vector{NTuple{3,float(FT)}}, Vector{NTuple{3,Int}}) and the same vertex/face order.
+#
+# NOTE: Julia is not installed in the build image, so this file could not be executed there; every call it
+# makes is mirrored one-to-one by the Python host (meshing.jl_b200/api.py + capi.py), which IS tested against
+# the library on a B200.  Layout facts relied upon: Vector{NTuple{3,Float32}} == float[3n],
+# Vector{NTuple{3,Float64}} == double[3n], Vector{NTuple{3,Int}} == int64_t[3n] (isbits tuples are stored inline).
+#
+# There is no CPU fallback: anything but a dense Array{Float32,3} raises ArgumentError.
+module B200Meshing
+
+export isosurface, MarchingCubes, MarchingTetrahedra
+
+const libb200iso = get(ENV, "B200ISO_LIB", joinpath(@__DIR__, "..", "lib", "libb200iso.so"))
+
+abstract type AbstractMeshingAlgorithm end
+Base.@kwdef struct MarchingCubes{T} <: AbstractMeshingAlgorithm
+    iso::T = 0.0
+end
+Base.@kwdef struct MarchingTetrahedra{T,E} <: AbstractMeshingAlgorithm
+    iso::T = 0.0
+    eps::E = 1e-3
+end
+
+# struct b200iso_params (include/b200iso.h)
+struct Params
+    algo::Int32
+    iso_is_f32::Int32
+    eps_is_f32::Int32
+    range_kind::Int32
+    iso::Float64
+    eps::Float64
+    x0::Float64; x1::Float64
+    y0::Float64; y1::Float64
+    z0::Float64; z1::Float64
+    x_offset::Int64
+    nx_global::Int64
+end
+
+const B200ISO_MC, B200ISO_MT = Int32(0), Int32(1)
+const B200ISO_HOST, B200ISO_DEVICE = Cint(0), Cint(1)
+
+last_error() = unsafe_string(ccall((:b200iso_last_error, libb200iso), Cstring, ()))
+check(rc) = rc == 0 ? nothing : error("b200iso error $rc: $(last_error())")
+
+# one handle per thread (a handle is not thread-safe); created lazily on device B200ISO_DEVICE (default 0)
+const handles = Dict{Int,Ptr{Cvoid}}()
+function handle()
+    get!(handles, Threads.threadid()) do
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:b200iso_create, libb200iso), Cint, (Ref{Ptr{Cvoid}}, Cint), h, parse(Cint, get(ENV, "B200ISO_DEVICE", "0"))))
+        h[]
+    end
+end
+
+# typeof(iso)/typeof(eps): Float32 stays Float32; Float64 stays Float64; an Integer behaves like Float32 next to
+# a Float32 field (promote_type(Int, Float32) == Float32) and must be exact in Float32.
+scalar_kind(v::Float32) = (Float64(v), Int32(1))
+scalar_kind(v::Float64) = (v, Int32(0))
+function scalar_kind(v::Integer)
+    Float32(v) == v || throw(ArgumentError("integer level $v is not exact in Float32"))
+    (Float64(v), Int32(1))
+end
+scalar_kind(v) = throw(ArgumentError("unsupported level type $(typeof(v)) on the B200 path"))
+
+range_kind(::Type{<:Integer}) = Int32(0)
+range_kind(::Type{Float32}) = Int32(1)
+range_kind(::Type{Float64}) = Int32(2)
+range_kind(T) = throw(ArgumentError("unsupported range element type $T on the B200 path"))
+
+function params(method, X, Y, Z)
+    kx, ky, kz = range_kind(typeof(first(X))), range_kind(typeof(first(Y))), range_kind(typeof(first(Z)))
+    kx == ky == kz || throw(ArgumentError("X, Y, Z must share an element type on the B200 path"))
+    iso, isf = scalar_kind(method.iso)
+    if method isa MarchingCubes
+        algo, eps, epf = B200ISO_MC, 1e-3, Int32(1)
+    else
+        algo = B200ISO_MT
+        eps, epf = scalar_kind(method.eps)
+    end
+    Params(algo, isf, epf, kx, iso, eps, first(X), last(X), first(Y), last(Y), first(Z), last(Z), 0, 0)
+end
+
+vertex_eltype(p::Params) =
+    (p.iso_is_f32 == 0 || p.range_kind == 2 || (p.algo == B200ISO_MT && p.eps_is_f32 == 0)) ? Float64 : Float32
+
+function _isosurface(sdf::Array{Float32,3}, method, X, Y, Z)
+    nx, ny, nz = size(sdf)
+    p = Ref(params(method, X, Y, Z))
+    h = handle()
+    nv, nf, f64 = Ref{Int64}(0), Ref{Int64}(0), Ref{Cint}(0)
+    GC.@preserve sdf begin
+        check(ccall((:b200iso_count, libb200iso), Cint,
+                    (Ptr{Cvoid}, Ref{Params}, Ptr{Float32}, Cint, Int64, Int64, Int64, Int64, Ref{Int64}, Ref{Int64}, Ref{Cint}),
+                    h, p, pointer(sdf), B200ISO_HOST, nx, ny, nz, nx, nv, nf, f64))
+    end
+    VT = vertex_eltype(p[])
+    @assert (f64[] != 0) == (VT === Float64)
+    vts = Vector{NTuple{3,VT}}(undef, nv[])
+    fcs = Vector{NTuple{3,Int}}(undef, nf[])
+    GC.@preserve vts fcs begin
+        check(ccall((:b200iso_generate, libb200iso), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Cint, Int64),
+                    h, pointer(vts), pointer(fcs), B200ISO_HOST, 0))
+    end
+    vts, fcs
+end
+
+# same positional signature and defaults as the reference
+function isosurface(sdf::AbstractArray{T,3}, method::Union{MarchingCubes,MarchingTetrahedra}, X=-1:1, Y=-1:1, Z=-1:1) where {T}
+    sdf isa Array{Float32,3} ||
+        throw(ArgumentError("the B200 path accepts a dense Array{Float32,3} (got $(typeof(sdf))); there is no CPU fallback"))
+    _isosurface(sdf, method, X, Y, Z)
+end
+# src/isosurface.jl:30-32
+isosurface(A::AbstractArray{T,3}, args...) where {T} = isosurface(A, MarchingCubes(), args...)
+
+end # module
