@@ -119,6 +119,10 @@ int b200iso_totals(b200iso_handle* h, int64_t* nverts, int64_t* nfaces, int* ver
 int b200iso_extract_async(b200iso_handle* h, const b200iso_params* p, const float* sdf_dev, int64_t nx, int64_t ny,
                           int64_t nz, int64_t ldx, void* verts_dev, int64_t vcap, int64_t* faces_dev, int64_t fcap,
                           const int64_t* vertex_base_dev, int64_t vertex_base, int64_t* totals_dev);
+/* Strategy of b200iso_extract_async for Marching Cubes (results are identical):
+ *   0 = (default) classify, count+scan, generate back to back -- the fastest measured form
+ *   1 = classify, then ONE fused count/scan/generate kernel (decoupled look-back inside generate) */
+int b200iso_set_extract_mode(b200iso_handle* h, int mode);
 int b200iso_add_vertex_base_async(b200iso_handle* h, int64_t* faces_dev, int64_t fcap, const int64_t* totals_dev,
                                   const int64_t* vertex_base_dev);
 

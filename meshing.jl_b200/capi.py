@@ -71,6 +71,7 @@ def load():
     L.b200iso_totals.argtypes = [vp, pi64, pi64, pci]
     L.b200iso_extract_async.argtypes = [vp, pp, vp, i64, i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]
     L.b200iso_add_vertex_base_async.argtypes = [vp, vp, i64, vp, vp]
+    L.b200iso_set_extract_mode.argtypes = [vp, ci]
     L.b200iso_case_indices.argtypes = [vp, vp, ci]
     L.b200iso_enable_timing.argtypes = [vp, ci]
     L.b200iso_timings.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ci]
@@ -136,6 +137,10 @@ class Handle:
                                             ctypes.c_void_p(verts_dev_ptr), vcap, ctypes.c_void_p(faces_dev_ptr), fcap,
                                             ctypes.c_void_p(vertex_base_dev_ptr or 0), vertex_base,
                                             ctypes.c_void_p(totals_dev_ptr or 0)))
+
+    def set_extract_mode(self, mode):
+        """0 = count then generate (default), 1 = fused single-pass kernel"""
+        _check(self.L.b200iso_set_extract_mode(self.h, mode))
 
     def add_vertex_base_async(self, faces_dev_ptr, fcap, totals_dev_ptr, vertex_base_dev_ptr):
         _check(self.L.b200iso_add_vertex_base_async(self.h, ctypes.c_void_p(faces_dev_ptr), fcap,

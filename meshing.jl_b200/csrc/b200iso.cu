@@ -75,6 +75,8 @@ struct b200iso_handle {
   DevBuf<uint32_t> bits;
   DevBuf<uint32_t> celloff;      // MT: per-cell vertex prefix inside its block
   DevBuf<unsigned long long> status;
+  DevBuf<unsigned long long> woff;  // MC: exclusive (vertex, face) prefix of every generate block
+  long long chain_blocks = 0;       // blocks of the look-back chain of the last count
   DevBuf<double> coords;
   DevBuf<float> field;           // staging of a host field
   DevBuf<unsigned char> vstage;  // staging of vertices for host output
@@ -99,6 +101,7 @@ struct b200iso_handle {
   unsigned char* ev_set = nullptr;    // which events of a slot were recorded
   long long step = 0;                 // steps (count calls) since timing was enabled
   int64_t launches = 0;
+  int mode = 0;  // b200iso_extract_async strategy for MC: 0 = count then generate, 1 = fused single pass
   int rec(int which) {
     if (!timing) return 0;
     const int slot = (int)((step > 0 ? step - 1 : 0) % NSLOT);
@@ -156,7 +159,11 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const float* sdf_d
   }
   const size_t nbits = (size_t)nx * ny * g.W;
   if (int rc = h->bits.reserve(nbits)) return rc;
-  if (int rc = h->status.reserve((size_t)h->nblocks * 2)) return rc;
+  const bool warp_count = p->algo == B200ISO_MC && !fused;
+  h->chain_blocks = warp_count ? (h->nblocks + iso::WC_THREADS / 32 - 1) / (iso::WC_THREADS / 32) : h->nblocks;
+  if (int rc = h->status.reserve((size_t)h->chain_blocks * 2)) return rc;
+  if (warp_count)
+    if (int rc = h->woff.reserve((size_t)h->nblocks * 2)) return rc;
   if (p->algo == B200ISO_MT)
     if (int rc = h->celloff.reserve(nbits)) return rc;
   if (int rc = h->coords.reserve((size_t)(nx + ny + nz))) return rc;
@@ -180,12 +187,13 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const float* sdf_d
   }
   if (int rc = h->rec(b200iso_handle::E_C1)) return rc;
   // (2) count + decoupled look-back scan (in the fused form the generate kernel does this itself)
-  CU(cudaMemsetAsync(h->status.p, 0, (size_t)h->nblocks * 2 * sizeof(unsigned long long), st));
+  CU(cudaMemsetAsync(h->status.p, 0, (size_t)h->chain_blocks * 2 * sizeof(unsigned long long), st));
   CU(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int), st));
   h->totals_out = totals_out;
   if (fused) {
   } else if (p->algo == B200ISO_MC)
-    iso::count_kernel<0><<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->status.p, h->ticket, h->nblocks, h->totals_dev, totals_out, nullptr);
+    iso::mc_count_warp_kernel<<<(unsigned)h->chain_blocks, iso::WC_THREADS, 0, st>>>(h->bits.p, g, h->nblocks, h->status.p, h->ticket,
+                                                                                   h->chain_blocks, h->totals_dev, totals_out, h->woff.p);
   else
     iso::count_kernel<1><<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->status.p, h->ticket, h->nblocks, h->totals_dev, totals_out, h->celloff.p);
   CU(cudaGetLastError());
@@ -212,7 +220,7 @@ int enqueue_generate(b200iso_handle* h, void* verts_dev, int64_t vcap, int64_t* 
   if (h->nblocks > 0) {
     const b200iso_params& p = h->prm;
     iso::GenArgs a{};
-    a.sdf = h->sdf_dev, a.bits = h->bits.p, a.status = h->status.p, a.coords = h->coords.p;
+    a.sdf = h->sdf_dev, a.bits = h->bits.p, a.status = h->status.p, a.woff = h->woff.p, a.coords = h->coords.p;
     a.verts = verts_dev, a.faces = (long long*)faces_dev, a.vcap = vcap, a.fcap = fcap;
     a.vbase_dev = (const long long*)vertex_base_dev, a.vbase = vertex_base;
     a.iso_d = p.iso, a.iso_f = (float)p.iso, a.eps_d = p.eps, a.eps_f = (float)p.eps;
@@ -280,7 +288,7 @@ int b200iso_destroy(b200iso_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  h->bits.release(), h->celloff.release(), h->status.release(), h->coords.release(), h->field.release(), h->vstage.release(), h->fstage.release();
+  h->bits.release(), h->celloff.release(), h->woff.release(), h->status.release(), h->coords.release(), h->field.release(), h->vstage.release(), h->fstage.release();
   if (h->ticket) cudaFree(h->ticket);
   if (h->totals_dev) cudaFree(h->totals_dev);
   if (h->totals_host) cudaFreeHost(h->totals_host);
@@ -333,7 +341,7 @@ int b200iso_extract_async(b200iso_handle* h, const b200iso_params* p, const floa
   if (vcap < 0 || fcap < 0) return fail(B200ISO_EINVAL, "negative capacity");
   if ((vcap > 0 && !verts_dev) || (fcap > 0 && !faces_dev)) return fail(B200ISO_EINVAL, "output pointer is NULL");
   CU(cudaSetDevice(h->device));
-  const bool fused = p->algo == B200ISO_MC;
+  const bool fused = p->algo == B200ISO_MC && h->mode == 1;
   if (int rc = enqueue_count(h, p, sdf_dev, nx, ny, nz, ldx, (long long*)totals_dev, false, fused)) return rc;
   return enqueue_generate(h, verts_dev, vcap, faces_dev, fcap, vertex_base_dev, vertex_base, fused);
 }
@@ -480,5 +488,11 @@ int b200iso_timings(b200iso_handle* h, float* ms, int n) {
 }
 
 int64_t b200iso_launch_count(b200iso_handle* h) { return h ? h->launches : 0; }
+
+int b200iso_set_extract_mode(b200iso_handle* h, int mode) {
+  if (!h || mode < 0 || mode > 1) return fail(B200ISO_EINVAL, "bad handle or mode");
+  h->mode = mode;
+  return 0;
+}
 
 }  // extern "C"

@@ -79,4 +79,84 @@ count_kernel(const uint32_t* __restrict__ bits, Grid g, unsigned long long* stat
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Marching Cubes count, warp-autonomous: a warp walks one generate block's quad-cells (lane <-> quad-cell,
+// 32 at a time), only the per-block publication to the look-back chain needs a barrier; the exclusive
+// (vertex, face) prefix of EVERY generate block is written to `woff`.
+constexpr int WC_THREADS = 256;  // 8 warps = 8 generate blocks per chain block
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(WC_THREADS)
+mc_count_warp_kernel(const uint32_t* __restrict__ bits, Grid g, long long nchunks, unsigned long long* status, unsigned int* ticket,
+                     long long nblocks, long long* totals_a, long long* totals_b, unsigned long long* __restrict__ woff) {
+  __shared__ uint8_t nf_s[256];
+  __shared__ uint32_t wv_s[WC_THREADS / 32], wf_s[WC_THREADS / 32];
+  __shared__ unsigned sb;
+  if (threadIdx.x == 0) sb = atomicAdd(ticket, 1u);
+  nf_s[threadIdx.x] = (uint8_t)((ISO_MC_VERTS[threadIdx.x] >> 52) & 7);
+  __syncthreads();
+  const unsigned b = sb;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long chunk = (long long)b * (WC_THREADS / 32) + w;
+  uint32_t nv = 0, nf = 0;
+  if (chunk < nchunks) {
+    // chunk == generate block: CB_THREADS consecutive quad-cells of one voxel x-row, walked 32 at a time
+    const int x = (int)(chunk / g.blocks_per_row);
+    const int q_lo = (int)(chunk - (long long)x * g.blocks_per_row) * CB_THREADS;
+    for (int q0 = q_lo; q0 < q_lo + CB_THREADS && q0 < g.quads_per_row; q0 += 32) {
+      TMap tm;
+      const int qr = q0 + lane;
+      tm.x = x, tm.y = qr / g.Wq, tm.zq = qr - tm.y * g.Wq, tm.live = qr < g.quads_per_row;
+      Quad q;
+      if (tm.live && load_quad(bits, g, tm.x, tm.y, tm.zq, q)) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t mm = active_mask(q, i);
+          if (mm) {
+            nv += mc_nverts_masked(q, i, q.vm[i]);
+            while (mm) {
+              const int k = __ffs(mm) - 1;
+              mm &= mm - 1;
+              nf += nf_s[case_of<0>(q, i, k)];
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nv += __shfl_xor_sync(0xffffffffu, nv, o);
+    nf += __shfl_xor_sync(0xffffffffu, nf, o);
+  }
+  if (lane == 0) wv_s[w] = nv, wf_s[w] = nf;
+  __syncthreads();
+  if (w == 0) {
+    // per-warp exclusive prefixes inside the block, block aggregate, look-back, publish
+    const uint32_t mv = lane < WC_THREADS / 32 ? wv_s[lane] : 0u, mf = lane < WC_THREADS / 32 ? wf_s[lane] : 0u;
+    const uint32_t iv = warp_incl_scan(mv), jf = warp_incl_scan(mf);
+    const unsigned long long av = __shfl_sync(0xffffffffu, iv, 31), af = __shfl_sync(0xffffffffu, jf, 31);
+    unsigned long long ev, ef;
+    lookback(status, (long long)b, av, af, ev, ef);
+    const long long cc = (long long)b * (WC_THREADS / 32) + lane;
+    if (lane < WC_THREADS / 32 && cc < nchunks) {
+      woff[2 * cc] = ev + (iv - mv);
+      woff[2 * cc + 1] = ef + (jf - mf);
+    }
+    if ((long long)b == nblocks - 1 && lane == 0) {
+      totals_a[0] = (long long)(ev + av), totals_a[1] = (long long)(ef + af);
+      if (totals_b) totals_b[0] = (long long)(ev + av), totals_b[1] = (long long)(ef + af);
+    }
+  }
+}
+
 }  // namespace iso

@@ -408,7 +408,8 @@ __global__ void case_kernel(const uint32_t* __restrict__ bits, Grid g, uint8_t* 
 struct GenArgs {
   const float* sdf;
   const uint32_t* bits;
-  const unsigned long long* status;  // inclusive prefixes per block (after count_kernel)
+  const unsigned long long* status;  // look-back chain state (MT / fused: inclusive prefixes per block)
+  const unsigned long long* woff;    // MC two-kernel form: exclusive (vertex, face) prefix of every generate block
   const double* coords;              // xp | yp | zp
   void* verts;
   long long* faces;
@@ -453,17 +454,15 @@ __device__ __forceinline__ void mc_interp(const GenArgs& a, float va, float vb, 
     }
   }
 }
-constexpr int GEN_NB = CB_THREADS;     // active voxels per dense round (one per thread)
-constexpr int GEN_MAXV = GEN_NB * 12;  // vertices of a round (MC: <= 12 per voxel)
-constexpr int GEN_MAXF = GEN_NB * 5;   // faces of a round (MC: <= 5 per voxel)
+constexpr int GEN_NB = 2 * CB_THREADS;  // active voxels per dense round (two records per thread)
+constexpr int GEN_MAXV = GEN_NB * 12;   // vertices of a round (MC: <= 12 per voxel)
+constexpr int GEN_MAXF = GEN_NB * 5;    // faces of a round (MC: <= 5 per voxel)
 
 // Pushes the (y,z | case) records of this thread's active voxels whose position in the block's scan order
-// falls in [lo, hi).  `a0` = position of the thread's first active voxel.
+// falls in [lo, hi).  `a0` = position of the thread's first active voxel, q = its (already loaded) quad-cell.
 template <int ALGO>
-__device__ __forceinline__ void push_records(const uint32_t* __restrict__ bits, const Grid& g, const TMap& tm, uint32_t a0,
-                                             uint32_t lo, uint32_t hi, uint32_t* rec_yz, uint8_t* rec_c) {
-  Quad q;
-  if (!load_quad(bits, g, tm.x, tm.y, tm.zq, q)) return;
+__device__ __forceinline__ void push_records(const Quad& q, const TMap& tm, uint32_t a0, uint32_t lo, uint32_t hi,
+                                             uint32_t* rec_yz, uint8_t* rec_c) {
   uint32_t idx = a0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -485,15 +484,12 @@ __device__ __forceinline__ void push_records(const uint32_t* __restrict__ bits, 
   }
 }
 
-// number of active voxels of this thread's quad-cell
-__device__ __forceinline__ uint32_t count_active(const uint32_t* __restrict__ bits, const Grid& g, const TMap& tm) {
+// loads the thread's quad-cell (kept in registers for the first window) and counts its active voxels
+__device__ __forceinline__ uint32_t count_active(const uint32_t* __restrict__ bits, const Grid& g, const TMap& tm, Quad& q) {
   uint32_t na = 0;
-  if (tm.live) {
-    Quad q;
-    if (load_quad(bits, g, tm.x, tm.y, tm.zq, q)) {
+  if (tm.live && load_quad(bits, g, tm.x, tm.y, tm.zq, q)) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) na += __popc(active_mask(q, i));
-    }
+    for (int i = 0; i < 4; ++i) na += __popc(active_mask(q, i));
   }
   return na;
 }
@@ -514,12 +510,9 @@ __device__ __forceinline__ unsigned block_id(unsigned int* ticket, unsigned* s_b
 template <bool FUSED>
 __device__ __forceinline__ void block_base(const GenArgs& a, unsigned b, unsigned long long tot_v, unsigned long long tot_f,
                                            unsigned long long* s_base, unsigned long long& bv, unsigned long long& bf) {
-  if (!FUSED) {
-    bv = bf = 0;
-    if (b > 0) {
-      bv = a.status[2 * (unsigned long long)(b - 1)] & VAL_MASK;
-      bf = a.status[2 * (unsigned long long)(b - 1) + 1] & VAL_MASK;
-    }
+  if (!FUSED) {  // exclusive prefixes of every generate block, written by mc_count_warp_kernel
+    bv = a.woff[2 * (unsigned long long)b];
+    bf = a.woff[2 * (unsigned long long)b + 1];
     return;
   }
   if (threadIdx.x < 32) {
@@ -558,7 +551,8 @@ mc_generate_kernel(GenArgs a, Grid g) {
   const unsigned b = block_id<FUSED>(a.ticket, &s_b);
   const TMap tm = thread_map(g, b);
   // ---- A: active voxels per thread, exclusive scan (thread order == scan order) ----
-  const uint32_t tna = count_active(a.bits, g, tm);
+  Quad q;
+  const uint32_t tna = count_active(a.bits, g, tm, q);
   uint32_t blk_na;
   const uint32_t my_a0 = block_excl_scan_u32(tna, s_w, blk_na);
   if (blk_na == 0) {  // uniform: nothing crosses this block
@@ -582,10 +576,10 @@ mc_generate_kernel(GenArgs a, Grid g) {
     uint32_t tv = 0, tf = 0;
     for (uint32_t lo = 0; lo < blk_na; lo += GEN_NB) {
       const uint32_t hi = min(lo + (uint32_t)GEN_NB, blk_na);
-      if (tna && my_a0 < hi && my_a0 + tna > lo) push_records<0>(a.bits, g, tm, my_a0, lo, hi, rec_yz, rec_c);
+      if (tna && my_a0 < hi && my_a0 + tna > lo) push_records<0>(q, tm, my_a0, lo, hi, rec_yz, rec_c);
       __syncthreads();
-      if ((uint32_t)tid < hi - lo) {
-        const unsigned long long t = tabV[rec_c[tid]];
+      for (uint32_t s = tid; s < hi - lo; s += CB_THREADS) {
+        const unsigned long long t = tabV[rec_c[s]];
         tv += (uint32_t)((t >> 48) & 15), tf += (uint32_t)((t >> 52) & 7);
       }
       __syncthreads();
@@ -597,8 +591,7 @@ mc_generate_kernel(GenArgs a, Grid g) {
     have_base = true;
   }
   const long long vbase = a.vbase + (a.vbase_dev ? *a.vbase_dev : 0);
-  const double* yp = a.coords + g.nx;
-  const double* zp = a.coords + g.nx + g.ny;
+  const unsigned yofs = (unsigned)g.nx, zofs = (unsigned)(g.nx + g.ny);  // coords = xp | yp | zp
   const double x0d = __ldg(a.coords + tm.x), x1d = __ldg(a.coords + tm.x + 1);
   V* verts = reinterpret_cast<V*>(a.verts);
   const int x = tm.x;
@@ -606,29 +599,48 @@ mc_generate_kernel(GenArgs a, Grid g) {
   for (uint32_t lo = 0; lo < blk_na; lo += GEN_NB) {
     const uint32_t hi = min(lo + (uint32_t)GEN_NB, blk_na);
     const uint32_t cnt = hi - lo;
-    // ---- B1a: records (position, case) of the window's voxels, in scan order ----
-    if (tna && my_a0 < hi && my_a0 + tna > lo) push_records<0>(a.bits, g, tm, my_a0, lo, hi, rec_yz, rec_c);
+    // ---- B1a: records (position, case) of the window's voxels, in scan order; the case index of an
+    //      active voxel is computed exactly once, here ----
+    if (tna && my_a0 < hi && my_a0 + tna > lo) push_records<0>(q, tm, my_a0, lo, hi, rec_yz, rec_c);
     __syncthreads();
-    // ---- B1b: thread per voxel: counts -> scan -> owner maps; gather the 8 corner samples ----
-    uint32_t nv = 0, nf = 0;
-    if ((uint32_t)tid < cnt) {
-      const unsigned long long tv = tabV[rec_c[tid]];
-      nv = (uint32_t)((tv >> 48) & 15), nf = (uint32_t)((tv >> 52) & 7);
-      const uint32_t yz = rec_yz[tid];
-      const float* p = a.sdf + x + g.ldx * (long long)(yz & 0xffffu) + g.plane * (long long)(yz >> 16);
-      const float c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + g.ldx + 1), c3 = __ldg(p + g.ldx);
-      const float* p1 = p + g.plane;
-      const float c4 = __ldg(p1), c5 = __ldg(p1 + 1), c6 = __ldg(p1 + g.ldx + 1), c7 = __ldg(p1 + g.ldx);
-      *reinterpret_cast<float4*>(&corner[tid][0]) = make_float4(c0, c1, c2, c3);
-      *reinterpret_cast<float4*>(&corner[tid][4]) = make_float4(c4, c5, c6, c7);
+    // ---- B1b: two records per thread: counts -> scan -> owner maps; gather the 8 corner samples ----
+    const uint32_t r0 = 2 * tid, r1 = r0 + 1;
+    uint32_t nv0 = 0, nf0 = 0, nv1 = 0, nf1 = 0;
+    if (r0 < cnt) {
+      const unsigned long long tv = tabV[rec_c[r0]];
+      nv0 = (uint32_t)((tv >> 48) & 15), nf0 = (uint32_t)((tv >> 52) & 7);
+    }
+    if (r1 < cnt) {
+      const unsigned long long tv = tabV[rec_c[r1]];
+      nv1 = (uint32_t)((tv >> 48) & 15), nf1 = (uint32_t)((tv >> 52) & 7);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const uint32_t rr = r0 + r;
+      if (rr < cnt) {
+        const uint32_t yz = rec_yz[rr];
+        const float* p = a.sdf + x + g.ldx * (long long)(yz & 0xffffu) + g.plane * (long long)(yz >> 16);
+        const float c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + g.ldx + 1), c3 = __ldg(p + g.ldx);
+        const float* p1 = p + g.plane;
+        const float c4 = __ldg(p1), c5 = __ldg(p1 + 1), c6 = __ldg(p1 + g.ldx + 1), c7 = __ldg(p1 + g.ldx);
+        *reinterpret_cast<float4*>(&corner[rr][0]) = make_float4(c0, c1, c2, c3);
+        *reinterpret_cast<float4*>(&corner[rr][4]) = make_float4(c4, c5, c6, c7);
+      }
     }
     uint32_t wtot;
-    const uint32_t ex = block_excl_scan_u32(nv | (nf << 16), s_w, wtot);
-    if ((uint32_t)tid < cnt) {
+    const uint32_t ex = block_excl_scan_u32((nv0 + nv1) | ((nf0 + nf1) << 16), s_w, wtot);
+    {
       const uint32_t v0 = ex & 0xffffu, f0 = ex >> 16;
-      rec_v[tid] = (uint16_t)v0, rec_f[tid] = (uint16_t)f0;
-      for (uint32_t i = 0; i < nv; ++i) owner_v[v0 + i] = (uint8_t)tid;
-      for (uint32_t i = 0; i < nf; ++i) owner_f[f0 + i] = (uint8_t)tid;
+      if (r0 < cnt) {
+        rec_v[r0] = (uint16_t)v0, rec_f[r0] = (uint16_t)f0;
+        for (uint32_t i = 0; i < nv0; ++i) owner_v[v0 + i] = (uint8_t)r0;
+        for (uint32_t i = 0; i < nf0; ++i) owner_f[f0 + i] = (uint8_t)r0;
+      }
+      if (r1 < cnt) {
+        rec_v[r1] = (uint16_t)(v0 + nv0), rec_f[r1] = (uint16_t)(f0 + nf0);
+        for (uint32_t i = 0; i < nv1; ++i) owner_v[v0 + nv0 + i] = (uint8_t)r1;
+        for (uint32_t i = 0; i < nf1; ++i) owner_f[f0 + nf0 + i] = (uint8_t)r1;
+      }
     }
     const uint32_t nvr = wtot & 0xffffu, nfr = wtot >> 16;
     if (FUSED && !have_base) {  // single window: its totals are the block totals
@@ -640,7 +652,7 @@ mc_generate_kernel(GenArgs a, Grid g) {
 
     // ---- B2: thread per vertex (vertex_interp, src/marching_cubes.jl:100-104) ----
     for (uint32_t k = tid; k < nvr; k += CB_THREADS) {
-      const uint32_t s = owner_v[k];
+      const uint32_t s = owner_v[k];  // record index 0..255
       const uint32_t c = rec_c[s], yz = rec_yz[s];
       const uint32_t which = k - rec_v[s];
       const uint32_t e = (uint32_t)(tabV[c] >> (4 * which)) & 15u;
@@ -649,10 +661,16 @@ mc_generate_kernel(GenArgs a, Grid g) {
       // MC corner offsets (dx | dy<<1 | dz<<2) for corners 0..7: 0,1,3,2,4,5,7,6
       const uint32_t oa = (0x67542310u >> (4 * ca)) & 7u, ob = (0x67542310u >> (4 * cb)) & 7u;
       const float va = corner[s][ca], vb = corner[s][cb];
-      const int vy = (int)(yz & 0xffffu), vz = (int)(yz >> 16);
-      const double y0d = __ldg(yp + vy), y1d = __ldg(yp + vy + 1), z0d = __ldg(zp + vz), z1d = __ldg(zp + vz + 1);
-      const double pa[3] = {(oa & 1u) ? x1d : x0d, (oa & 2u) ? y1d : y0d, (oa & 4u) ? z1d : z0d};
-      const double pb[3] = {(ob & 1u) ? x1d : x0d, (ob & 2u) ? y1d : y0d, (ob & 4u) ? z1d : z0d};
+      const unsigned vy = yofs + (yz & 0xffffu), vz = zofs + (yz >> 16);
+      double pa[3], pb[3];
+      pa[0] = (oa & 1u) ? x1d : x0d;
+      pa[1] = __ldg(a.coords + (vy + ((oa >> 1) & 1u)));
+      pa[2] = __ldg(a.coords + (vz + (oa >> 2)));
+      const uint32_t df = oa ^ ob;  // the one axis along which the edge runs
+      pb[0] = (ob & 1u) ? x1d : x0d;
+      pb[1] = pa[1], pb[2] = pa[2];
+      if (df & 2u) pb[1] = __ldg(a.coords + (vy + ((ob >> 1) & 1u)));
+      if (df & 4u) pb[2] = __ldg(a.coords + (vz + (ob >> 2)));
       double p[3];
       mc_interp<MODE>(a, va, vb, pa, pb, p);
       const long long gi = (long long)bv + k;

@@ -124,7 +124,11 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
   const TMap tm = thread_map(g, b);
   const int x = tm.x;
   // ---- A: active voxels per thread, exclusive scan (thread order == scan order) ----
-  const uint32_t tna = count_active(a.bits, g, tm);
+  uint32_t tna;
+  {
+    Quad qc;  // (not kept: the MT kernel is register-bound, the push reloads the quad-cell through L1)
+    tna = count_active(a.bits, g, tm, qc);
+  }
   uint32_t blk_na;
   const uint32_t my_a0 = block_excl_scan_u32(tna, s_w, blk_na);
   if (blk_na == 0) return;
@@ -153,7 +157,11 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
     const uint32_t hi = min(lo + (uint32_t)MTG_NB, blk_na);
     const uint32_t cnt = hi - lo;
     // ---- B1a: records (position, case) of the window's voxels, in scan order ----
-    if (tna && my_a0 < hi && my_a0 + tna > lo) push_records<1>(a.bits, g, tm, my_a0, lo, hi, rec_yz, rec_c);
+    if (tna && my_a0 < hi && my_a0 + tna > lo) {
+      Quad qp;
+      load_quad(a.bits, g, tm.x, tm.y, tm.zq, qp);
+      push_records<1>(qp, tm, my_a0, lo, hi, rec_yz, rec_c);
+    }
     __syncthreads();
     // ---- B1b: thread per voxel: counts -> scan -> owner maps ----
     uint32_t nv = 0, nf = 0;

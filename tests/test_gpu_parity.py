@@ -259,9 +259,12 @@ def test_tall_grids(pkg, oracle, algo, shape):
     _check(pkg, oracle, pkg.synth.noise(shape, seed=9), algo, iso=0.9)
 
 
-@pytest.mark.parametrize("shape,kind", [((48, 40, 56), "gyroid"), ((33, 21, 300), "noise"), ((20, 130, 37), "sphere"), ((3, 3, 3), "noise")])
-def test_fused_single_pass_extract(pkg, oracle, shape, kind):
-    """b200iso_extract_async: classify + ONE count/scan/generate kernel (decoupled look-back inside generate)."""
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("shape,kind", [((48, 40, 56), "gyroid"), ((33, 21, 300), "noise"), ((20, 130, 37), "sphere"), ((3, 3, 3), "noise"),
+                                        ((300, 24, 70), "gyroid"), ((129, 9, 33), "noise"), ((515, 6, 40), "gyroid")])
+def test_fused_single_pass_extract(pkg, oracle, shape, kind, mode):
+    """b200iso_extract_async in both strategies: 0 = kernels back to back, 1 = fused count/scan/generate kernel
+    (decoupled look-back inside generate)."""
     import torch
     s = getattr(pkg.synth, kind)(shape)
     vo, fo = oracle.isosurface(s, 0, iso_is_f32=True)
@@ -273,6 +276,7 @@ def test_fused_single_pass_extract(pkg, oracle, shape, kind):
     verts = torch.full((len(vo) + 3, 3), -7.0, dtype=torch.float32, device="cuda")
     faces = torch.full((len(fo) + 3, 3), -7, dtype=torch.int64, device="cuda")
     h.set_stream(torch.cuda.current_stream().cuda_stream)
+    h.set_extract_mode(mode)
     for _ in range(2):  # twice: the scan state must be reset between calls
         h.extract_async(p, t.data_ptr(), nx, ny, nz, nx, verts.data_ptr(), verts.shape[0], faces.data_ptr(), faces.shape[0], 0, 0,
                         totals.data_ptr())

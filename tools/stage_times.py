@@ -6,10 +6,12 @@ import numpy as np, torch
 from __graft_entry__ import load_package
 pkg = load_package()
 algo = sys.argv[1] if len(sys.argv) > 1 else "MC"
-fused = "fused" in sys.argv
+fused = any(a.startswith("mode") for a in sys.argv)
+mode = int([a for a in sys.argv if a.startswith("mode")][0][4:]) if fused else 0
 sizes = [int(a) for a in sys.argv[2:] if a.isdigit()] or [256, 512, 1024]
 h = pkg.capi.Handle(0)
 h.enable_timing(True)
+h.set_extract_mode(mode)
 for n in sizes:
     t = pkg.synth.gyroid_torch(n, "cuda")
     torch.cuda.synchronize()
@@ -27,7 +29,17 @@ for n in sizes:
             h.generate(verts.data_ptr(), faces.data_ptr(), pkg.capi.DEVICE, 0)
         tm = h.timings()
     tot = tm["classify_ms"] + tm["count_scan_ms"] + tm["generate_ms"]
+    if fused:
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h.set_stream(torch.cuda.current_stream().cuda_stream)
+        e0.record()
+        for _ in range(10):
+            h.extract_async(p, t.data_ptr(), n, n, n, t.stride(1), verts.data_ptr(), nv, faces.data_ptr(), nf)
+        e1.record(); torch.cuda.synchronize()
+        tot = e0.elapsed_time(e1) / 10
+        h.use_own_stream()
     B = 4 * n ** 3 + 12 * nv + 24 * nf
-    print(f"{algo}{" fused" if fused else ""} n={n} nv={nv} nf={nf} classify={tm['classify_ms']:.3f} count={tm['count_scan_ms']:.3f} gen={tm['generate_ms']:.3f} "
+    print(f"{algo}{" mode%d" % mode if fused else ""} n={n} nv={nv} nf={nf} classify={tm['classify_ms']:.3f} count={tm['count_scan_ms']:.3f} gen={tm['generate_ms']:.3f} "
           f"total={tot:.3f} ms  {(n-1)**3/tot/1e6:.1f} Gvox/s  {B/tot/1e6:.0f} GB/s  classify {4*n**3/tm['classify_ms']/1e6:.0f} GB/s", flush=True)
     del t, verts, faces
