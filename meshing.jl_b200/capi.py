@@ -9,7 +9,7 @@ import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "lib", "libb200iso.so")
+LIB_PATH = os.environ.get("B200ISO_LIB") or os.path.join(_HERE, "lib", "libb200iso.so")  # env override: A/B builds
 HEADER = os.path.join(ROOT, "include", "b200iso.h")
 
 MC, MT = 0, 1

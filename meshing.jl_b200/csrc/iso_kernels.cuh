@@ -45,7 +45,13 @@ struct Grid {
   long long plane;       // ldx * ny
 };
 
-constexpr int CB_THREADS = 128;  // threads (= quad-cells) per count/generate block
+#ifndef ISO_CB_THREADS
+#define ISO_CB_THREADS 128
+#endif
+#ifndef ISO_GEN_MINB
+#define ISO_GEN_MINB (1024 / ISO_CB_THREADS)
+#endif
+constexpr int CB_THREADS = ISO_CB_THREADS;  // threads (= quad-cells) per count/generate block
 
 inline void grid_setup(Grid& g, long long nx, long long ny, long long nz, long long ldx) {
   g.nx = (int)nx, g.ny = (int)ny, g.nz = (int)nz;
@@ -534,7 +540,7 @@ __device__ __forceinline__ void block_base(const GenArgs& a, unsigned b, unsigne
 // FUSED = true : classify-output -> mesh in ONE pass: count, decoupled look-back scan and generate fused
 //                (outputs must have capacity; totals are written by the last block).
 template <int MODE, typename V, bool FUSED>
-__global__ void __launch_bounds__(CB_THREADS, 1024 / CB_THREADS)
+__global__ void __launch_bounds__(CB_THREADS, ISO_GEN_MINB)
 mc_generate_kernel(GenArgs a, Grid g) {
   __shared__ unsigned long long tabV[256], tabF[256];
   __shared__ unsigned long long s_base[2];

@@ -94,7 +94,10 @@ constexpr int MTG_EDGES = 13;            // <= 13 crossed edges per voxel
 // A32: promote_type(typeof(iso), typeof(eps)) == Float32 (vertPos weights in Float32), else Float64.
 // P32: points (ranges) are Float32.  V: vertex element type.
 template <bool A32, bool P32, typename V>
-__global__ void __launch_bounds__(CB_THREADS)
+#ifndef ISO_MT_MINB
+#define ISO_MT_MINB 8
+#endif
+__global__ void __launch_bounds__(CB_THREADS, ISO_MT_MINB)
 mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
   __shared__ unsigned long long own0_s[256];   // ISO_MT_OWNED[c][flags = 0]
   __shared__ unsigned long long faces_s[768];  // ISO_MT_FACES
