@@ -83,13 +83,22 @@ __device__ __forceinline__ TMap thread_map(const Grid& g, unsigned b) {
 
 // ------------------------------------------------------------------------------------------------------
 // (1) signpack
-constexpr int SP_WARPS = 4;
+#ifndef ISO_SP_WARPS
+#define ISO_SP_WARPS 4
+#endif
+constexpr int SP_WARPS = ISO_SP_WARPS;
 constexpr int SP_XSEG = 128;   // samples of one row handled by a warp (one float4 per lane)
-constexpr int SP_ZW = 8;       // z-words per warp task (8 words = one 32-byte sector per column)
+#ifndef ISO_SP_ZW
+#define ISO_SP_ZW 16
+#endif
+constexpr int SP_ZW = ISO_SP_ZW;  // z-words per warp task (16 words = 64 contiguous bytes per column; 8 measured 6% slower: 32-byte scattered writes)
 
 __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
   float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.f32 {%0,%1,%2,%3}, [%4];"
+#ifndef ISO_SP_L2HINT
+#define ISO_SP_L2HINT "L2::128B"
+#endif
+  asm volatile("ld.global.nc.L1::no_allocate." ISO_SP_L2HINT ".v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(p));
   return v;
@@ -130,16 +139,19 @@ signpack_kernel(const float* __restrict__ sdf, uint32_t* __restrict__ bits, int 
       const bool full = zb + 32 <= nz;
       if (VEC) {
         const bool xin = xs < nx;
+#ifndef ISO_SP_U
+#define ISO_SP_U 8
+#endif
 #pragma unroll
-        for (int kb = 0; kb < 32; kb += 8) {
-          float4 v[8];
+        for (int kb = 0; kb < 32; kb += ISO_SP_U) {
+          float4 v[ISO_SP_U];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < ISO_SP_U; ++u) {
             const bool ok = xin && (full || zb + kb + u < nz);
             v[u] = ok ? ldg_stream_f4(p + (long long)(kb + u) * plane) : make_float4(qnan, qnan, qnan, qnan);
           }
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < ISO_SP_U; ++u) {
             w0 |= (v[u].x < thresh) ? (1u << (kb + u)) : 0u;
             w1 |= (v[u].y < thresh) ? (1u << (kb + u)) : 0u;
             w2 |= (v[u].z < thresh) ? (1u << (kb + u)) : 0u;
@@ -185,8 +197,9 @@ signpack_kernel(const float* __restrict__ sdf, uint32_t* __restrict__ bits, int 
       uint32_t c[SP_ZW];
 #pragma unroll
       for (int zw = 0; zw < SP_ZW; ++zw) c[zw] = j == 0 ? r[zw].x : j == 1 ? r[zw].y : j == 2 ? r[zw].z : r[zw].w;
-      if (wofs < W) *reinterpret_cast<uint4*>(dst) = make_uint4(c[0], c[1], c[2], c[3]);
-      if (wofs + 4 < W) *reinterpret_cast<uint4*>(dst + 4) = make_uint4(c[4], c[5], c[6], c[7]);
+#pragma unroll
+      for (int c4 = 0; c4 < SP_ZW; c4 += 4)
+        if (wofs + c4 < W) *reinterpret_cast<uint4*>(dst + c4) = make_uint4(c[c4], c[c4 + 1], c[c4 + 2], c[c4 + 3]);
     }
   }
 }
