@@ -366,7 +366,7 @@ def main():
         peak, peak_src = measured_peak()
         vbytes = 24 if f64 else 12
         alg = {"classify": 4.0 * nxl * ny * nz, "count_scan": 0.0, "generate": float(vbytes * nv + 24 * nf)}
-        kname = {"classify": "signpack_kernel", "count_scan": "count_kernel", "generate": "mc_generate_kernel" if spec["algo"] == "MC" else "mt_generate_kernel"}
+        kname = {"classify": "signpack_kernel", "count_scan": "mc_count_warp_kernel" if spec["algo"] == "MC" else "count_kernel", "generate": "mc_generate_kernel" if spec["algo"] == "MC" else "mt_generate_kernel"}
         stage_ms = {"classify": stage["classify_ms"], "count_scan": stage["count_scan_ms"], "generate": stage["generate_ms"]}
         dom = max(stage_ms, key=lambda k: stage_ms[k])
         achieved = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
@@ -387,6 +387,10 @@ def main():
                          "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic(kname[dom], args.workload),
                          "algorithmic_bytes_per_launch": alg[dom], "kernel_ms": stage_ms[dom],
                          "stage_ms": stage_ms,
+                         "kernels": {kname[k]: {"ms": stage_ms[k], "algorithmic_bytes": alg[k],
+                                                "achieved": (alg[k] / (stage_ms[k] * 1e-3) / 1e9 if stage_ms[k] > 0 else 0.0),
+                                                "frac": (alg[k] / (stage_ms[k] * 1e-3) / 1e9 / peak if stage_ms[k] > 0 else 0.0),
+                                                "traffic": ncu_traffic(kname[k], args.workload)} for k in stage_ms},
                          "pipeline": {"algorithmic_bytes_per_step": bytes_step, "achieved": pipe_gbs, "frac_of_measured": pipe_gbs / peak,
                                       "frac_of_nominal_8TBs": pipe_gbs / 8000.0}},
             "gpu_launches": int(launches),
