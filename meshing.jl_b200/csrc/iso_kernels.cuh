@@ -560,7 +560,7 @@ mc_generate_kernel(GenArgs a, Grid g) {
   __shared__ uint32_t s_w[CB_THREADS / 32];
   __shared__ unsigned s_b;
   __shared__ uint32_t rec_yz[GEN_NB];
-  __shared__ uint16_t rec_v[GEN_NB], rec_f[GEN_NB];
+  __shared__ uint32_t rec_pk[GEN_NB];  // case | local vertex offset << 8 | local face offset << 20
   __shared__ uint8_t rec_c[GEN_NB];
   __shared__ __align__(16) float corner[GEN_NB][8];
   __shared__ uint8_t owner_v[GEN_MAXV], owner_f[GEN_MAXF];
@@ -651,12 +651,12 @@ mc_generate_kernel(GenArgs a, Grid g) {
     {
       const uint32_t v0 = ex & 0xffffu, f0 = ex >> 16;
       if (r0 < cnt) {
-        rec_v[r0] = (uint16_t)v0, rec_f[r0] = (uint16_t)f0;
+        rec_pk[r0] = (uint32_t)rec_c[r0] | (v0 << 8) | (f0 << 20);
         for (uint32_t i = 0; i < nv0; ++i) owner_v[v0 + i] = (uint8_t)r0;
         for (uint32_t i = 0; i < nf0; ++i) owner_f[f0 + i] = (uint8_t)r0;
       }
       if (r1 < cnt) {
-        rec_v[r1] = (uint16_t)(v0 + nv0), rec_f[r1] = (uint16_t)(f0 + nf0);
+        rec_pk[r1] = (uint32_t)rec_c[r1] | ((v0 + nv0) << 8) | ((f0 + nf0) << 20);
         for (uint32_t i = 0; i < nv1; ++i) owner_v[v0 + nv0 + i] = (uint8_t)r1;
         for (uint32_t i = 0; i < nf1; ++i) owner_f[f0 + nf0 + i] = (uint8_t)r1;
       }
@@ -669,12 +669,14 @@ mc_generate_kernel(GenArgs a, Grid g) {
       __syncthreads();
     }
 
+    // capacity guard hoisted: the whole window fits in the output buffers in all but the overflow case
+    const bool vfits = (long long)bv + nvr <= a.vcap, ffits = (long long)bf + nfr <= a.fcap;
     // ---- B2: thread per vertex (vertex_interp, src/marching_cubes.jl:100-104) ----
     for (uint32_t k = tid; k < nvr; k += CB_THREADS) {
       const uint32_t s = owner_v[k];  // record index 0..255
-      const uint32_t c = rec_c[s], yz = rec_yz[s];
-      const uint32_t which = k - rec_v[s];
-      const uint32_t e = (uint32_t)(tabV[c] >> (4 * which)) & 15u;
+      const uint32_t pk = rec_pk[s], yz = rec_yz[s];
+      const uint32_t which = k - ((pk >> 8) & 0xfffu);
+      const uint32_t e = (uint32_t)(tabV[pk & 0xffu] >> (4 * which)) & 15u;
       const uint32_t cc = edge_c[e];
       const uint32_t ca = cc & 15u, cb = cc >> 4;
       // MC corner offsets (dx | dy<<1 | dz<<2) for corners 0..7: 0,1,3,2,4,5,7,6
@@ -692,21 +694,19 @@ mc_generate_kernel(GenArgs a, Grid g) {
       if (df & 4u) pb[2] = __ldg(a.coords + (vz + (ob >> 2)));
       double p[3];
       mc_interp<MODE>(a, va, vb, pa, pb, p);
-      const long long gi = (long long)bv + k;
-      if (gi < a.vcap) {
-        V* o = verts + 3 * gi;
+      if (vfits || (long long)bv + k < a.vcap) {
+        V* o = verts + 3 * ((long long)bv + k);
         o[0] = (V)p[0], o[1] = (V)p[1], o[2] = (V)p[2];
       }
     }
     // ---- B3: thread per face ----
     for (uint32_t k = tid; k < nfr; k += CB_THREADS) {
-      const uint32_t s = owner_f[k];
-      const uint32_t fi = k - rec_f[s];
-      const uint32_t tri = (uint32_t)(tabF[rec_c[s]] >> (12 * fi)) & 0xfffu;
-      const long long fct = vbase + (long long)bv + rec_v[s] + 1;  // 1-based index of the voxel's first vertex
-      const long long gi = (long long)bf + k;
-      if (gi < a.fcap) {
-        long long* o = a.faces + 3 * gi;
+      const uint32_t pk = rec_pk[owner_f[k]];
+      const uint32_t fi = k - (pk >> 20);
+      const uint32_t tri = (uint32_t)(tabF[pk & 0xffu] >> (12 * fi)) & 0xfffu;
+      const long long fct = vbase + (long long)bv + ((pk >> 8) & 0xfffu) + 1;  // 1-based index of the voxel's first vertex
+      if (ffits || (long long)bf + k < a.fcap) {
+        long long* o = a.faces + 3 * ((long long)bf + k);
         o[0] = fct + (tri & 15u), o[1] = fct + ((tri >> 4) & 15u), o[2] = fct + ((tri >> 8) & 15u);
       }
     }
