@@ -102,6 +102,9 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
   __shared__ unsigned long long own0_s[256];   // ISO_MT_OWNED[c][flags = 0]
   __shared__ unsigned long long faces_s[768];  // ISO_MT_FACES
   __shared__ uint32_t cross_s[256];
+  __shared__ unsigned long long clist_s[256];  // ISO_MT_CROSSLIST
+  __shared__ uint32_t rank0_s[256];            // ISO_MT_RANK0
+  __shared__ uint8_t slot_s[20];               // ISO_MT_OWN_SLOT
   __shared__ uint8_t nown0_s[256], nf_s[256];
   __shared__ uint16_t einfo_s[20];
   __shared__ uint8_t eshift_s[160];
@@ -118,9 +121,11 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
     nown0_s[i] = ISO_MT_NOWN[i * 8];
     nf_s[i] = ISO_MT_NF[i];
     cross_s[i] = ISO_MT_CROSS[i];
+    clist_s[i] = ISO_MT_CROSSLIST[i];
+    rank0_s[i] = ISO_MT_RANK0[i];
   }
   for (int i = tid; i < 768; i += CB_THREADS) faces_s[i] = ISO_MT_FACES[i];
-  for (int i = tid; i < 20; i += CB_THREADS) einfo_s[i] = ISO_MT_EDGE_INFO[i];
+  for (int i = tid; i < 20; i += CB_THREADS) einfo_s[i] = ISO_MT_EDGE_INFO[i], slot_s[i] = ISO_MT_OWN_SLOT[i];
   for (int i = tid; i < 160; i += CB_THREADS) eshift_s[i] = ISO_MT_EDGE_SHIFT[i];
 
   const unsigned b = blockIdx.x;
@@ -191,16 +196,21 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
       const uint32_t c = vc >> 24;
       const uint32_t cm = cross_s[c];
       if (j >= (uint32_t)__popc(cm)) continue;
-      const int e = __fns(cm, 0, j + 1) + 1;  // j-th crossed edge, 1..19
+      // j-th crossed edge (ascending id), 1..19: from the per-case list; a 13th is the highest crossed edge
+      const int e = j < 12 ? (int)((clist_s[c] >> (5 * j)) & 31u) : 32 - __clz(cm);
       const int vy = (int)(yz & 0xffffu), vz = (int)(yz >> 16);
       const int flags = fx | (vy == 0 ? 2 : 0) | (vz == 0 ? 4 : 0);
       const int low = (einfo_s[e] >> 6) & 7;
       const int sh = low & ~flags;  // axes on which the owner is the previous voxel
       int32_t id;
       if (sh == 0) {  // this voxel owns the edge
-        const unsigned long long ow = owned_word(c, flags);
         int r = 0;
-        while (((ow >> (5 * r)) & 31u) != (unsigned)e) ++r;
+        if (flags == 0) {  // interior voxel: rank of an interior-owned edge from the per-case table
+          r = (int)((rank0_s[c] >> (3 * slot_s[e])) & 7u);
+        } else {
+          const unsigned long long ow = owned_word(c, flags);
+          while (((ow >> (5 * r)) & 31u) != (unsigned)e) ++r;
+        }
         id = (int32_t)(vc & 0xffffffu) + r;
       } else {
         const int ox = x - (sh & 1), oy = vy - ((sh >> 1) & 1), oz = vz - (sh >> 2);
@@ -210,9 +220,13 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
         load_cell(a.bits, g, ox, oy, oz >> 5, q);
         const int k = oz & 31;
         const uint32_t oc = case_of<1>(q, 0, k);
-        const unsigned long long ow = owned_word(oc, oflags);
         int r = 0;
-        while (((ow >> (5 * r)) & 31u) != (unsigned)eo) ++r;
+        if (oflags == 0) {
+          r = (int)((rank0_s[oc] >> (3 * slot_s[eo])) & 7u);
+        } else {
+          const unsigned long long ow = owned_word(oc, oflags);
+          while (((ow >> (5 * r)) & 31u) != (unsigned)eo) ++r;
+        }
         // vertices created before the owner voxel: block prefix + cell prefix + in-cell prefix
         const uint32_t below = q.vm[0] & ((1u << k) - 1u);
         const uint32_t incell = mt_owned_masked(q, 0, below, oflags & 3, (oz >> 5) == 0);
