@@ -1,0 +1,171 @@
+// signpack_tma.cuh -- classify (sign-pack) with TMA staging: cp.async.bulk.tensor 3-D boxes + mbarrier pipeline.
+//
+// Same task decomposition and output as signpack_kernel (iso_kernels.cuh): a warp owns (128-sample x-segment, y,
+// 512-z chunk).  Instead of per-lane 128-bit loads, lane 0 of every warp keeps TM_STAGES TMA boxes in flight
+// (box = 128 x * 1 y * TM_BZ z Float32 = 4 KB, landing dense in the warp's slice of shared memory, completion on
+// an mbarrier with expect_tx); the 32 lanes then read conflict-free LDS.128 rows and build the z-packed words.
+// Out-of-range samples (x >= nx, z >= nz) are filled with NaN by the tensor map (NaN < iso is false, like the
+// reference's compare), so no lane-side bounds logic is needed.  Each warp runs its own pipeline: no block barrier.
+#pragma once
+#include <cuda.h>
+
+#include "iso_kernels.cuh"
+
+namespace iso {
+
+#ifndef ISO_TM_WARPS
+#define ISO_TM_WARPS 4
+#endif
+#ifndef ISO_TM_BZ
+#define ISO_TM_BZ 8
+#endif
+#ifndef ISO_TM_STAGES
+#define ISO_TM_STAGES 4
+#endif
+constexpr int TM_WARPS = ISO_TM_WARPS;    // warps per CTA, each with a private pipeline
+constexpr int TM_BZ = ISO_TM_BZ;          // z-planes per TMA box
+constexpr int TM_STAGES = ISO_TM_STAGES;  // boxes in flight per warp
+constexpr int TM_BOX_FLOATS = SP_XSEG * TM_BZ;                 // 1024 floats = 4 KB
+constexpr int TM_BOXES = SP_ZW * 32 / TM_BZ;                   // boxes per warp task
+constexpr size_t TM_SMEM_PER_WARP = (size_t)TM_STAGES * TM_BOX_FLOATS * 4 + (size_t)SP_ZW * SP_XSEG * 4;
+constexpr size_t TM_SMEM = TM_WARPS * TM_SMEM_PER_WARP + 128;  // + alignment slack
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__global__ void __launch_bounds__(TM_WARPS * 32)
+signpack_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t* __restrict__ bits, int nx, int ny, int nz, int W,
+                    float thresh, int nxseg, long long ntasks) {
+  extern __shared__ __align__(128) unsigned char tm_smem[];
+  __shared__ __align__(8) uint64_t full[TM_WARPS][TM_STAGES];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long task = (long long)blockIdx.x * TM_WARPS + wib;
+  if (task >= ntasks) return;
+  unsigned char* base = tm_smem + (128 - (smem_u32(tm_smem) & 127)) % 128 + (size_t)wib * TM_SMEM_PER_WARP;
+  float* box = reinterpret_cast<float*>(base);                                                      // [TM_STAGES][TM_BZ][128]
+  uint32_t* wstage = reinterpret_cast<uint32_t*>(base + (size_t)TM_STAGES * TM_BOX_FLOATS * 4);      // [SP_ZW][128]
+  const int xseg = (int)(task % nxseg);
+  const long long t2 = task / nxseg;
+  const int y = (int)(t2 % ny);
+  const int zc = (int)(t2 / ny);
+  const int x0 = xseg * SP_XSEG, z0 = zc * SP_ZW * 32;
+  // boxes of this task that contain at least one valid z-plane
+  const int nbox = min(TM_BOXES, (nz - z0 + TM_BZ - 1) / TM_BZ);
+
+  if (lane == 0) {
+    for (int s = 0; s < TM_STAGES; ++s) mbar_init(&full[wib][s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int s = 0; s < TM_STAGES && s < nbox; ++s) {
+      mbar_expect_tx(&full[wib][s], TM_BOX_FLOATS * 4);
+      tma_load_3d(box + s * TM_BOX_FLOATS, &tmap, x0, y, z0 + s * TM_BZ, &full[wib][s]);
+    }
+  }
+  __syncwarp();
+
+  uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+  for (int b = 0; b < TM_BOXES; ++b) {
+    const int s = b % TM_STAGES;
+    if (b < nbox) {
+      mbar_wait(&full[wib][s], (uint32_t)((b / TM_STAGES) & 1));
+      const float4* row = reinterpret_cast<const float4*>(box + s * TM_BOX_FLOATS) + lane;
+      const int sh = (b * TM_BZ) & 31;
+#pragma unroll
+      for (int k = 0; k < TM_BZ; ++k) {
+        const float4 v = row[k * (SP_XSEG / 4)];
+        w0 |= (v.x < thresh) ? (1u << (sh + k)) : 0u;
+        w1 |= (v.y < thresh) ? (1u << (sh + k)) : 0u;
+        w2 |= (v.z < thresh) ? (1u << (sh + k)) : 0u;
+        w3 |= (v.w < thresh) ? (1u << (sh + k)) : 0u;
+      }
+      __syncwarp();  // every lane has read the stage: it may be overwritten
+      if (lane == 0 && b + TM_STAGES < nbox) {
+        mbar_expect_tx(&full[wib][s], TM_BOX_FLOATS * 4);
+        tma_load_3d(box + s * TM_BOX_FLOATS, &tmap, x0, y, z0 + (b + TM_STAGES) * TM_BZ, &full[wib][s]);
+      }
+    }
+    if (((b + 1) * TM_BZ) % 32 == 0) {  // a z-word is complete
+      *reinterpret_cast<uint4*>(&wstage[(b * TM_BZ / 32) * SP_XSEG + lane * 4]) = make_uint4(w0, w1, w2, w3);
+      w0 = w1 = w2 = w3 = 0;
+    }
+  }
+  // write-out, identical to signpack_kernel<true>: column j of this lane, SP_ZW words as 16-byte stores
+  uint4 r[SP_ZW];
+#pragma unroll
+  for (int zw = 0; zw < SP_ZW; ++zw) r[zw] = *reinterpret_cast<const uint4*>(&wstage[zw * SP_XSEG + lane * 4]);
+  const int wofs = zc * SP_ZW;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int x = x0 + lane * 4 + j;
+    if (x < nx) {
+      uint32_t* dst = bits + ((long long)x * ny + y) * W + wofs;
+      uint32_t c[SP_ZW];
+#pragma unroll
+      for (int zw = 0; zw < SP_ZW; ++zw) c[zw] = j == 0 ? r[zw].x : j == 1 ? r[zw].y : j == 2 ? r[zw].z : r[zw].w;
+#pragma unroll
+      for (int c4 = 0; c4 < SP_ZW; c4 += 4)
+        if (wofs + c4 < W) *reinterpret_cast<uint4*>(dst + c4) = make_uint4(c[c4], c[c4 + 1], c[c4 + 2], c[c4 + 3]);
+    }
+  }
+}
+
+// Host side: tensor map over the field (x innermost), encoded through the driver entry point (no libcuda link).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn tma_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+// returns false when the field cannot be described by a tensor map (caller falls back to the LDG kernel)
+inline bool make_field_tmap(CUtensorMap* map, const float* sdf, long long nx, long long ny, long long nz, long long ldx) {
+  EncodeTiledFn fn = tma_encode_fn();
+  if (!fn) return false;
+  if ((reinterpret_cast<uintptr_t>(sdf) & 15) != 0 || ldx % 4 != 0) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz};
+  const cuuint64_t strides[2] = {(cuuint64_t)ldx * 4, (cuuint64_t)ldx * ny * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)SP_XSEG, 1, (cuuint32_t)TM_BZ};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  if (strides[1] >= (1ull << 40)) return false;
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(sdf), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA) == CUDA_SUCCESS;
+}
+
+}  // namespace iso
