@@ -366,7 +366,8 @@ def main():
         peak, peak_src = measured_peak()
         vbytes = 24 if f64 else 12
         alg = {"classify": 4.0 * nxl * ny * nz, "count_scan": 0.0, "generate": float(vbytes * nv + 24 * nf)}
-        tma = ncu_traffic("signpack_tma_kernel", args.workload) is not None and nxl * ny * nz >= (1 << 28)
+        w16 = ((nz + 31) // 32 + 15) // 16
+        tma = ((nxl + 127) // 128) * ny * w16 >= 4096 and os.environ.get("B200ISO_TMA", "1") != "0"  # the library's rule
         kname = {"classify": "signpack_tma_kernel" if tma else "signpack_kernel", "count_scan": "mc_count_warp_kernel" if spec["algo"] == "MC" else "count_kernel", "generate": "mc_generate_kernel" if spec["algo"] == "MC" else "mt_generate_kernel"}
         stage_ms = {"classify": stage["classify_ms"], "count_scan": stage["count_scan_ms"], "generate": stage["generate_ms"]}
         dom = max(stage_ms, key=lambda k: stage_ms[k])

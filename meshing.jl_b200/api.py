@@ -184,20 +184,41 @@ def isosurface_slab(sdf_slab, method, x_offset, nx_global, vertex_base, *ranges,
 
 
 def slab_count(sdf_slab, method, x_offset, nx_global, *ranges, device=0):
-    a = np.asfortranarray(np.asarray(sdf_slab))
-    if a.dtype != np.float32 or a.ndim != 3:
-        raise TypeError("3-D Float32 field expected")
+    """Phase 1 of a slab: classify + count.  numpy slab (host) or x-contiguous CUDA torch slab (device-resident)."""
     if not isinstance(method, MarchingCubes):
         raise TypeError("x-slab sharding is implemented for MarchingCubes (MT runs as replicas)")
     params = make_params(method, *ranges)
     params.x_offset, params.nx_global = x_offset, nx_global
+    if _is_torch(sdf_slab):
+        import torch
+        t = sdf_slab
+        if t.dim() != 3 or t.dtype != torch.float32 or not t.is_cuda or (t.shape[0] > 1 and t.stride(0) != 1):
+            raise TypeError("torch slab must be a 3-D float32 CUDA tensor with x stride 1")
+        nx, ny, nz = t.shape
+        h = get_handle(t.device.index)
+        torch.cuda.current_stream(t.device).synchronize()  # the handle runs on its own stream
+        nv, nf, f64 = h.count(params, t.data_ptr(), capi.DEVICE, nx, ny, nz, t.stride(1) if ny > 1 else nx)
+        h._slab_device = t.device
+        return h, nv, nf, f64
+    a = np.asfortranarray(np.asarray(sdf_slab))
+    if a.dtype != np.float32 or a.ndim != 3:
+        raise TypeError("3-D Float32 field expected")
     nx, ny, nz = a.shape
     h = get_handle(device)
+    h._slab_device = None
     nv, nf, f64 = h.count(params, a.ctypes.data, capi.HOST, nx, ny, nz, nx)
     return h, nv, nf, f64
 
 
 def slab_generate(h, nv, nf, f64, vertex_base):
+    """Phase 2 of a slab: generate with the slab's global vertex base added to the face indices."""
+    dev = getattr(h, "_slab_device", None)
+    if dev is not None:
+        import torch
+        verts = torch.empty((nv, 3), dtype=torch.float64 if f64 else torch.float32, device=dev)
+        faces = torch.empty((nf, 3), dtype=torch.int64, device=dev)
+        h.generate(verts.data_ptr(), faces.data_ptr(), capi.DEVICE, vertex_base)
+        return verts, faces
     verts = np.empty((nv, 3), dtype=np.float64 if f64 else np.float32)
     faces = np.empty((nf, 3), dtype=np.int64)
     h.generate(verts.ctypes.data, faces.ctypes.data, capi.HOST, vertex_base)

@@ -315,3 +315,48 @@ def test_fused_extract_mt_falls_back_to_two_kernels(pkg, oracle):
     assert h.totals()[:2] == (len(vo), len(fo))
     assert _bits_equal(verts.cpu().numpy(), vo) and np.array_equal(faces.cpu().numpy(), fo)
     h.close()
+
+
+def test_full_size_1024_gyroid_properties(pkg, oracle):
+    """BASELINE.json configs[3] at its full size (1024^3 gyroid, MC, Float32 vertices), checked through
+    size-independent properties: (1) the totals equal the expectation of SURVEY.md Appendix C, (2) structural
+    invariants of the face array, (3) the 8-slab sharded extraction equals the one-shot extraction byte for byte
+    (a checksum of checksums over slabs), (4) the oracle agrees on sampled x-ranges of the volume."""
+    import torch
+    n = 1024
+    t = pkg.synth.gyroid_torch(n, "cuda")
+    m = pkg.MarchingCubes(iso=pkg.Float32(0))
+    v, f = pkg.isosurface(t, m)
+    assert v.shape == (40573677, 3) and f.shape == (20286967, 3) and v.dtype == torch.float32
+    assert int(f.min()) == 1 and int(f.max()) == v.shape[0]
+    assert bool(torch.isfinite(v).all()) and float(v.min()) >= -1.0 and float(v.max()) <= 1.0
+    # every voxel block starts with the face (fct+3, fct+2, fct+1): column 0 - column 2 == 2 exactly there
+    assert int(((f[:, 0] - f[:, 2]) == 2).sum()) >= 10143355  # >= number of active voxels (Appendix C)
+    # (3) sharded == unsharded
+    counts, slabs = [], []
+    for r in range(8):
+        xa, xb = pkg.sharding.slab_bounds(n, 8, r)
+        slabs.append((xa, xb))
+        _, nv, nf, _ = pkg.api.slab_count(t[xa:xb], m, xa, n)
+        counts.append((nv, nf))
+    assert sum(c[0] for c in counts) == v.shape[0] and sum(c[1] for c in counts) == f.shape[0]
+    vo = fo = 0
+    for r, (xa, xb) in enumerate(slabs):
+        vb, fb = pkg.sharding.exclusive_bases(counts, r)
+        assert (vb, fb) == (vo, fo)
+        sv, sf = pkg.api.isosurface_slab(t[xa:xb], m, xa, n, vb)
+        assert torch.equal(sv, v[vo: vo + sv.shape[0]]) and torch.equal(sf, f[fo: fo + sf.shape[0]])
+        vo += sv.shape[0]
+        fo += sf.shape[0]
+    # (4) oracle on three thin x-ranges (with their halo plane), coordinates of the whole volume
+    for xa in (0, 517, n - 6):
+        xb = xa + 6
+        host = np.asfortranarray(t[xa:xb].cpu().numpy())
+        gv, gf = pkg.api.isosurface_slab(host, m, xa, n, 0)
+        # oracle: same slab as an independent volume whose X range is the slab's part of [-1, 1]
+        xs = -1.0 + 2.0 * np.arange(n) / (n - 1)
+        ov, of = oracle.isosurface(host, 0, iso_is_f32=True, ranges=((float(xs[xa]), float(xs[xb - 1])), (-1, 1), (-1, 1)),
+                                   range_kind=oracle.RANGE_F64)
+        assert np.array_equal(gf, of)
+        assert gv.shape == ov.shape and np.array_equal(gv[:, 1:], ov[:, 1:].astype(np.float32))
+        assert np.abs(gv[:, 0].astype(np.float64) - ov[:, 0]).max() < 1e-6  # x: slab-local vs global LinRange rounding
