@@ -63,6 +63,11 @@ typedef struct b200iso_params {
    * (LinRange(first(X), last(X), nx_global)[x_offset + i]).  Both 0 for an unsharded call. */
   int64_t x_offset;
   int64_t nx_global;
+  /* element type of the field: 0 = Float32 (the fast path: TMA / 128-bit classify), 1 = Float64 (`sdf` then
+   * points to doubles; vertices are Float64, promote_type(..., Float64)).  Integer / Float16 fields are not
+   * accepted. */
+  int32_t field_is_f64;
+  int32_t reserved;
 } b200iso_params;
 
 /* ---- lifetime ------------------------------------------------------------------------------------ */
@@ -79,14 +84,14 @@ int b200iso_set_stream(b200iso_handle* h, void* cuda_stream);
 int b200iso_use_own_stream(b200iso_handle* h);
 
 /* ---- the drop-in pair: replaces the body of isosurface(sdf, method, X, Y, Z) ---------------------------
- * b200iso_count   : classify + count + scan.  `sdf` is Float32, host or device (mem), nx*ny*nz samples with
+ * b200iso_count   : classify + count + scan.  `sdf` is Float32 (Float64 if p->field_is_f64), host or device (mem), nx*ny*nz samples with
  *                   leading dimension ldx.  Reports the mesh size and the vertex element type
  *                   (vert_is_f64: 0 => Float32 triples, 1 => Float64 triples) so the caller can allocate
  *                   `Vector{NTuple{3,T}}(undef, nverts)` / `Vector{NTuple{3,Int}}(undef, nfaces)`.
  * b200iso_generate: writes 3*nverts vertex scalars and 3*nfaces Int64 indices into caller memory
  *                   (host or device).  `vertex_base` is added to every face index: 0 for a whole
  *                   volume, the global index base of the slab's first vertex for an x-slab shard. */
-int b200iso_count(b200iso_handle* h, const b200iso_params* p, const float* sdf, int mem, int64_t nx, int64_t ny,
+int b200iso_count(b200iso_handle* h, const b200iso_params* p, const void* sdf, int mem, int64_t nx, int64_t ny,
                   int64_t nz, int64_t ldx, int64_t* nverts, int64_t* nfaces, int* vert_is_f64);
 int b200iso_generate(b200iso_handle* h, void* verts, int64_t* faces, int mem, int64_t vertex_base);
 
@@ -99,7 +104,7 @@ int b200iso_generate(b200iso_handle* h, void* verts, int64_t* faces, int mem, in
  *                         The face index base is vertex_base + (vertex_base_dev ? *vertex_base_dev : 0),
  *                         read on the device when the kernel runs.
  * b200iso_totals        : synchronises the stream and returns the totals of the last count. */
-int b200iso_count_async(b200iso_handle* h, const b200iso_params* p, const float* sdf_dev, int64_t nx, int64_t ny,
+int b200iso_count_async(b200iso_handle* h, const b200iso_params* p, const void* sdf_dev, int64_t nx, int64_t ny,
                         int64_t nz, int64_t ldx, int64_t* totals_dev);
 int b200iso_generate_async(b200iso_handle* h, void* verts_dev, int64_t vcap, int64_t* faces_dev, int64_t fcap,
                            const int64_t* vertex_base_dev, int64_t vertex_base);
@@ -116,7 +121,7 @@ int b200iso_totals(b200iso_handle* h, int64_t* nverts, int64_t* nfaces, int* ver
  * b200iso_add_vertex_base_async: adds *vertex_base_dev to the first min(totals_dev[1], fcap) faces -- the
  *                        sharded fix-up when the slab's global vertex base (from the all-gather of the
  *                        slabs' totals) becomes known only after the slab was extracted. */
-int b200iso_extract_async(b200iso_handle* h, const b200iso_params* p, const float* sdf_dev, int64_t nx, int64_t ny,
+int b200iso_extract_async(b200iso_handle* h, const b200iso_params* p, const void* sdf_dev, int64_t nx, int64_t ny,
                           int64_t nz, int64_t ldx, void* verts_dev, int64_t vcap, int64_t* faces_dev, int64_t fcap,
                           const int64_t* vertex_base_dev, int64_t vertex_base, int64_t* totals_dev);
 /* Strategy of b200iso_extract_async for Marching Cubes (results are identical):

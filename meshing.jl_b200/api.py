@@ -13,7 +13,7 @@ Float64, Python `int` <-> Int.  `Float32` / `Float64` are exported as aliases, s
 the benchmark reads `isosurface(sdf, MarchingCubes(iso=Float32(0)))`.
 
 Everything is computed by libb200iso.so (CUDA, sm_100a).  Inputs the accelerated path does not cover
-(non-Float32 fields) raise TypeError -- there is no CPU fallback.
+(fields that are not Float32/Float64) raise TypeError -- there is no CPU fallback.
 """
 from dataclasses import dataclass
 from typing import Any
@@ -40,8 +40,9 @@ class MarchingTetrahedra:
 
 
 def _scalar_kind(v, what):
-    """-> (value as float, is_f32).  Int behaves like the other operands' type (Float32 here, because the
-    field is Float32: promote_type(Int64, Float32) == Float32), provided it is exact in Float32."""
+    """-> (value as float, is_f32).  An Int level takes the type of the other operands (promote_type(Int64,
+    Float32) == Float32; next to a Float64 field the Float32 flag is harmless: everything promotes to Float64),
+    provided it is exact in Float32."""
     if isinstance(v, (np.float32,)):
         return float(v), True
     if isinstance(v, (bool, np.bool_)):
@@ -117,7 +118,7 @@ def _is_torch(x):
 def isosurface(sdf, *args, device=None):
     """isosurface(sdf[, method][, X, Y, Z]) -> (vertices, faces)
 
-    sdf      : 3-D Float32 array, `sdf[x, y, z]`.  numpy array (host; any strides, made x-contiguous like a
+    sdf      : 3-D Float32 (fast path) or Float64 array, `sdf[x, y, z]`.  numpy array (host; any strides, made x-contiguous like a
                Julia Array) or a CUDA torch tensor whose x stride is 1 (device-resident: outputs are CUDA
                tensors too and nothing crosses PCIe).
     method   : MarchingCubes(iso=...) (default) or MarchingTetrahedra(iso=..., eps=...)
@@ -138,9 +139,10 @@ def isosurface(sdf, *args, device=None):
     a = np.asarray(sdf)
     if a.ndim != 3:
         raise TypeError("sdf must be a 3-D array")
-    if a.dtype != np.float32:
-        raise TypeError(f"the B200 path accepts Float32 fields only (got {a.dtype}); there is no CPU fallback")
+    if a.dtype not in (np.float32, np.float64):
+        raise TypeError(f"the B200 path accepts Float32 and Float64 fields (got {a.dtype}); there is no CPU fallback")
     a = np.asfortranarray(a)
+    params.field_is_f64 = int(a.dtype == np.float64)
     nx, ny, nz = a.shape
     h = get_handle(0 if device is None else device)
     nv, nf, f64 = h.count(params, a.ctypes.data, capi.HOST, nx, ny, nz, nx)
@@ -153,8 +155,9 @@ def isosurface(sdf, *args, device=None):
 def _isosurface_torch(t, params, device):
     import torch
 
-    if t.dim() != 3 or t.dtype != torch.float32 or not t.is_cuda:
-        raise TypeError("torch input must be a 3-D float32 CUDA tensor")
+    if t.dim() != 3 or t.dtype not in (torch.float32, torch.float64) or not t.is_cuda:
+        raise TypeError("torch input must be a 3-D float32/float64 CUDA tensor")
+    params.field_is_f64 = int(t.dtype == torch.float64)
     nx, ny, nz = t.shape
     sx, sy, sz = t.stride()
     if nx > 1 and sx != 1:
@@ -230,11 +233,13 @@ def case_indices(sdf, method=None, device=0):
     from the classify kernel's bit-field (parity check hook)."""
     method = method or MarchingCubes()
     a = np.asfortranarray(np.asarray(sdf))
-    if a.dtype != np.float32 or a.ndim != 3:
-        raise TypeError("3-D Float32 field expected")
+    if a.dtype not in (np.float32, np.float64) or a.ndim != 3:
+        raise TypeError("3-D Float32/Float64 field expected")
     nx, ny, nz = a.shape
     h = get_handle(device)
-    h.count(make_params(method), a.ctypes.data, capi.HOST, nx, ny, nz, nx)
+    params = make_params(method)
+    params.field_is_f64 = int(a.dtype == np.float64)
+    h.count(params, a.ctypes.data, capi.HOST, nx, ny, nz, nx)
     out = np.empty(max(nx - 1, 0) * max(ny - 1, 0) * max(nz - 1, 0), dtype=np.uint8)
     h.case_indices(out.ctypes.data, capi.HOST)
     return out

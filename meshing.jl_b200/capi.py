@@ -22,7 +22,8 @@ class Params(ctypes.Structure):
     _fields_ = [("algo", ctypes.c_int32), ("iso_is_f32", ctypes.c_int32), ("eps_is_f32", ctypes.c_int32),
                 ("range_kind", ctypes.c_int32), ("iso", ctypes.c_double), ("eps", ctypes.c_double),
                 ("x0", ctypes.c_double), ("x1", ctypes.c_double), ("y0", ctypes.c_double), ("y1", ctypes.c_double),
-                ("z0", ctypes.c_double), ("z1", ctypes.c_double), ("x_offset", ctypes.c_int64), ("nx_global", ctypes.c_int64)]
+                ("z0", ctypes.c_double), ("z1", ctypes.c_double), ("x_offset", ctypes.c_int64), ("nx_global", ctypes.c_int64),
+                ("field_is_f64", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class B200IsoError(RuntimeError):

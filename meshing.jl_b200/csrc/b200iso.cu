@@ -80,7 +80,7 @@ struct b200iso_handle {
   DevBuf<unsigned long long> woff;  // MC: exclusive (vertex, face) prefix of every generate block
   long long chain_blocks = 0;       // blocks of the look-back chain of the last count
   DevBuf<double> coords;
-  DevBuf<float> field;           // staging of a host field
+  DevBuf<unsigned char> field;   // staging of a host field
   DevBuf<unsigned char> vstage;  // staging of vertices for host output
   DevBuf<long long> fstage;
   unsigned int* ticket = nullptr;
@@ -90,7 +90,7 @@ struct b200iso_handle {
   bool counted = false, totals_known = false;
   b200iso_params prm{};
   iso::Grid grid{};
-  const float* sdf_dev = nullptr;
+  const void* sdf_dev = nullptr;
   long long* totals_out = nullptr;
   long long nblocks = 0;
   int vert_is_f64 = 0;
@@ -125,7 +125,7 @@ namespace {
 
 int vertex_is_f64(const b200iso_params& p) {
   // float(promote_type(eltype(X), eltype(Y), eltype(Z), Float32, typeof(iso)[, typeof(eps)]))
-  return (!p.iso_is_f32) || p.range_kind == B200ISO_RANGE_F64 || (p.algo == B200ISO_MT && !p.eps_is_f32);
+  return p.field_is_f64 || (!p.iso_is_f32) || p.range_kind == B200ISO_RANGE_F64 || (p.algo == B200ISO_MT && !p.eps_is_f32);
 }
 
 int check_params(const b200iso_params* p, int64_t nx, int64_t ny, int64_t nz, int64_t ldx) {
@@ -143,7 +143,7 @@ int check_params(const b200iso_params* p, int64_t nx, int64_t ny, int64_t nz, in
 }
 
 // fused = true: classify + coordinates only; the caller enqueues the single-pass generate kernel next.
-int enqueue_count(b200iso_handle* h, const b200iso_params* p, const float* sdf_dev, int64_t nx, int64_t ny, int64_t nz,
+int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_dev, int64_t nx, int64_t ny, int64_t nz,
                   int64_t ldx, long long* totals_out, bool step_begun = false, bool fused = false) {
   cudaStream_t st = h->stream;
   h->prm = *p;
@@ -175,7 +175,9 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const float* sdf_d
   if (int rc = h->rec(b200iso_handle::E_C0)) return rc;
   // (1) sign-pack
   {
-    const bool vec = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(sdf_dev) & 15) == 0);
+    const bool f64 = p->field_is_f64 != 0;
+    const bool vec = !f64 && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(sdf_dev) & 15) == 0);
+    const float* sdf_f = reinterpret_cast<const float*>(sdf_dev);
     const int nxseg = (int)((nx + iso::SP_XSEG - 1) / iso::SP_XSEG);
     const int nzc = (g.W + iso::SP_ZW - 1) / iso::SP_ZW;
     const long long ntasks = (long long)nxseg * ny * nzc;
@@ -184,7 +186,7 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const float* sdf_d
     CUtensorMap tmap;
     // (measured: TMA wins on big fields -- 0.656 vs 0.694 ms at 1024^3 -- and loses a few % when the grid is under two waves)
     const bool tma_wanted = h->tma_mode == 1 || (h->tma_mode < 0 && ntasks >= 4096);
-    if (vec && tma_wanted && iso::make_field_tmap(&tmap, sdf_dev, nx, ny, nz, ldx)) {
+    if (vec && tma_wanted && iso::make_field_tmap(&tmap, sdf_f, nx, ny, nz, ldx)) {
       // TMA-staged classify: same tasks, cp.async.bulk.tensor boxes + per-warp mbarrier pipeline
       static bool attr_set = false;
       if (!attr_set) {
@@ -194,9 +196,13 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const float* sdf_d
       const unsigned tb = (unsigned)((ntasks + iso::TM_WARPS - 1) / iso::TM_WARPS);
       iso::signpack_tma_kernel<<<tb, iso::TM_WARPS * 32, iso::TM_SMEM, st>>>(tmap, h->bits.p, g.nx, g.ny, g.nz, g.W, thr, nxseg, ntasks);
     } else if (vec)
-      iso::signpack_kernel<true><<<nb, iso::SP_WARPS * 32, 0, st>>>(sdf_dev, h->bits.p, g.nx, g.ny, g.nz, g.ldx, g.W, thr, nxseg, ntasks);
-    else
-      iso::signpack_kernel<false><<<nb, iso::SP_WARPS * 32, 0, st>>>(sdf_dev, h->bits.p, g.nx, g.ny, g.nz, g.ldx, g.W, thr, nxseg, ntasks);
+      iso::signpack_kernel<true, float><<<nb, iso::SP_WARPS * 32, 0, st>>>(sdf_f, h->bits.p, g.nx, g.ny, g.nz, g.ldx, g.W, thr, nxseg, ntasks);
+    else if (!f64)
+      iso::signpack_kernel<false, float><<<nb, iso::SP_WARPS * 32, 0, st>>>(sdf_f, h->bits.p, g.nx, g.ny, g.nz, g.ldx, g.W, thr, nxseg, ntasks);
+    else  // Float64 field: Float64 < promote(iso) compares exactly in Float64
+      iso::signpack_kernel<false, double><<<nb, iso::SP_WARPS * 32, 0, st>>>(reinterpret_cast<const double*>(sdf_dev), h->bits.p, g.nx, g.ny,
+                                                                           g.nz, g.ldx, g.W, p->iso_is_f32 ? (double)(float)p->iso : p->iso,
+                                                                           nxseg, ntasks);
     CU(cudaGetLastError());
     h->launches++;
   }
@@ -244,12 +250,14 @@ int enqueue_generate(b200iso_handle* h, void* verts_dev, int64_t vcap, int64_t* 
     const unsigned nb = (unsigned)h->nblocks;
     const bool pf32 = p.range_kind == B200ISO_RANGE_F32;
     if (p.algo == B200ISO_MC && fused) {
-      if (!p.iso_is_f32) iso::mc_generate_kernel<2, double, true><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+      if (p.field_is_f64) iso::mc_generate_kernel<3, double, true><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+      else if (!p.iso_is_f32) iso::mc_generate_kernel<2, double, true><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
       else if (pf32) iso::mc_generate_kernel<1, float, true><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
       else if (h->vert_is_f64) iso::mc_generate_kernel<0, double, true><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
       else iso::mc_generate_kernel<0, float, true><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
     } else if (p.algo == B200ISO_MC) {
-      if (!p.iso_is_f32) iso::mc_generate_kernel<2, double, false><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+      if (p.field_is_f64) iso::mc_generate_kernel<3, double, false><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+      else if (!p.iso_is_f32) iso::mc_generate_kernel<2, double, false><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
       else if (pf32) iso::mc_generate_kernel<1, float, false><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
       else if (h->vert_is_f64) iso::mc_generate_kernel<0, double, false><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
       else iso::mc_generate_kernel<0, float, false><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
@@ -330,7 +338,7 @@ int b200iso_use_own_stream(b200iso_handle* h) {
   return 0;
 }
 
-int b200iso_count_async(b200iso_handle* h, const b200iso_params* p, const float* sdf_dev, int64_t nx, int64_t ny,
+int b200iso_count_async(b200iso_handle* h, const b200iso_params* p, const void* sdf_dev, int64_t nx, int64_t ny,
                         int64_t nz, int64_t ldx, int64_t* totals_dev) {
   if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
   if (int rc = check_params(p, nx, ny, nz, ldx)) return rc;
@@ -348,7 +356,7 @@ int b200iso_generate_async(b200iso_handle* h, void* verts_dev, int64_t vcap, int
   return enqueue_generate(h, verts_dev, vcap, faces_dev, fcap, vertex_base_dev, vertex_base);
 }
 
-int b200iso_extract_async(b200iso_handle* h, const b200iso_params* p, const float* sdf_dev, int64_t nx, int64_t ny, int64_t nz,
+int b200iso_extract_async(b200iso_handle* h, const b200iso_params* p, const void* sdf_dev, int64_t nx, int64_t ny, int64_t nz,
                           int64_t ldx, void* verts_dev, int64_t vcap, int64_t* faces_dev, int64_t fcap,
                           const int64_t* vertex_base_dev, int64_t vertex_base, int64_t* totals_dev) {
   if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
@@ -385,26 +393,27 @@ int b200iso_totals(b200iso_handle* h, int64_t* nverts, int64_t* nfaces, int* ver
   return 0;
 }
 
-int b200iso_count(b200iso_handle* h, const b200iso_params* p, const float* sdf, int mem, int64_t nx, int64_t ny, int64_t nz,
+int b200iso_count(b200iso_handle* h, const b200iso_params* p, const void* sdf, int mem, int64_t nx, int64_t ny, int64_t nz,
                   int64_t ldx, int64_t* nverts, int64_t* nfaces, int* vert_is_f64) {
   if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
   if (int rc = check_params(p, nx, ny, nz, ldx)) return rc;
   if (mem != B200ISO_HOST && mem != B200ISO_DEVICE) return fail(B200ISO_EINVAL, "bad mem kind %d", mem);
   if (!sdf && nx * ny * nz > 0) return fail(B200ISO_EINVAL, "sdf is NULL");
   CU(cudaSetDevice(h->device));
-  const float* dev = sdf;
+  const void* dev = sdf;
   int64_t dldx = ldx;
+  const size_t esz = p->field_is_f64 ? 8 : 4;
   const bool staged = mem == B200ISO_HOST && nx * ny * nz > 0;
   if (staged) {
     // stage with a 16-byte aligned leading dimension so the 128-bit load path always applies
     dldx = (nx + 3) / 4 * 4;
-    if (int rc = h->field.reserve((size_t)dldx * ny * nz)) return rc;
+    if (int rc = h->field.reserve((size_t)dldx * ny * nz * esz)) return rc;
     h->begin_step();
     if (int rc = h->rec(b200iso_handle::E_H0)) return rc;
     if (dldx == ldx)
-      CU(cudaMemcpyAsync(h->field.p, sdf, (size_t)ldx * ny * nz * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+      CU(cudaMemcpyAsync(h->field.p, sdf, (size_t)ldx * ny * nz * esz, cudaMemcpyHostToDevice, h->stream));
     else
-      CU(cudaMemcpy2DAsync(h->field.p, (size_t)dldx * sizeof(float), sdf, (size_t)ldx * sizeof(float), (size_t)nx * sizeof(float),
+      CU(cudaMemcpy2DAsync(h->field.p, (size_t)dldx * esz, sdf, (size_t)ldx * esz, (size_t)nx * esz,
                            (size_t)ny * nz, cudaMemcpyHostToDevice, h->stream));
     if (int rc = h->rec(b200iso_handle::E_H1)) return rc;
     dev = h->field.p;

@@ -111,10 +111,11 @@ __device__ __forceinline__ float ldg_stream_f1(const float* p) {
 
 // VEC: rows are 16-byte aligned (ldx % 4 == 0, base aligned): lane owns columns 4*lane..4*lane+3.
 // !VEC: scalar loads, lane owns columns lane, lane+32, lane+64, lane+96 of the segment.
-template <bool VEC>
+// T = field element type: Float32 (both paths) or Float64 (scalar path only; the compare is then exact in Float64).
+template <bool VEC, typename T = float>
 __global__ void __launch_bounds__(SP_WARPS * 32)
-signpack_kernel(const float* __restrict__ sdf, uint32_t* __restrict__ bits, int nx, int ny, int nz, long long ldx,
-                int W, float thresh, int nxseg, long long ntasks) {
+signpack_kernel(const T* __restrict__ sdf, uint32_t* __restrict__ bits, int nx, int ny, int nz, long long ldx,
+                int W, T thresh, int nxseg, long long ntasks) {
   __shared__ __align__(16) uint32_t stage[SP_WARPS][SP_ZW][SP_XSEG];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long task = (long long)blockIdx.x * SP_WARPS + wib;
@@ -126,7 +127,7 @@ signpack_kernel(const float* __restrict__ sdf, uint32_t* __restrict__ bits, int 
   const long long plane = ldx * ny;
   const int xbase = xseg * SP_XSEG;
   const int xs = VEC ? xbase + lane * 4 : xbase + lane;
-  const float* rowp = sdf + (long long)y * ldx + xs;
+  const T* rowp = sdf + (long long)y * ldx + xs;
   const float qnan = __int_as_float(0x7fc00000);
 
 #pragma unroll 1
@@ -135,9 +136,9 @@ signpack_kernel(const float* __restrict__ sdf, uint32_t* __restrict__ bits, int 
     const int zb = zword * 32;
     uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
     if (zword < W && zb < nz) {
-      const float* p = rowp + (long long)zb * plane;
+      const T* p = rowp + (long long)zb * plane;
       const bool full = zb + 32 <= nz;
-      if (VEC) {
+      if (VEC && sizeof(T) == 4) {
         const bool xin = xs < nx;
 #ifndef ISO_SP_U
 #define ISO_SP_U 8
@@ -148,7 +149,7 @@ signpack_kernel(const float* __restrict__ sdf, uint32_t* __restrict__ bits, int 
 #pragma unroll
           for (int u = 0; u < ISO_SP_U; ++u) {
             const bool ok = xin && (full || zb + kb + u < nz);
-            v[u] = ok ? ldg_stream_f4(p + (long long)(kb + u) * plane) : make_float4(qnan, qnan, qnan, qnan);
+            v[u] = ok ? ldg_stream_f4(reinterpret_cast<const float*>(p + (long long)(kb + u) * plane)) : make_float4(qnan, qnan, qnan, qnan);
           }
 #pragma unroll
           for (int u = 0; u < ISO_SP_U; ++u) {
@@ -162,15 +163,15 @@ signpack_kernel(const float* __restrict__ sdf, uint32_t* __restrict__ bits, int 
         const bool in0 = xs < nx, in1 = xs + 32 < nx, in2 = xs + 64 < nx, in3 = xs + 96 < nx;
 #pragma unroll
         for (int kb = 0; kb < 32; kb += 4) {
-          float v[4][4];
+          T v[4][4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const bool zok = full || zb + kb + u < nz;
-            const float* q = p + (long long)(kb + u) * plane;
-            v[u][0] = (zok && in0) ? ldg_stream_f1(q) : qnan;
-            v[u][1] = (zok && in1) ? ldg_stream_f1(q + 32) : qnan;
-            v[u][2] = (zok && in2) ? ldg_stream_f1(q + 64) : qnan;
-            v[u][3] = (zok && in3) ? ldg_stream_f1(q + 96) : qnan;
+            const T* q = p + (long long)(kb + u) * plane;
+            v[u][0] = (zok && in0) ? __ldg(q) : (T)qnan;
+            v[u][1] = (zok && in1) ? __ldg(q + 32) : (T)qnan;
+            v[u][2] = (zok && in2) ? __ldg(q + 64) : (T)qnan;
+            v[u][3] = (zok && in3) ? __ldg(q + 96) : (T)qnan;
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -425,7 +426,7 @@ __global__ void case_kernel(const uint32_t* __restrict__ bits, Grid g, uint8_t* 
 //   2: iso::Float64: mu Float64, position Float64 (Float32 points are exact in Float64)
 // V = vertex element type (float / double), the reference's float(FT).
 struct GenArgs {
-  const float* sdf;
+  const void* sdf;  // Float32 field (Float64 for the *_f64 instantiations)
   const uint32_t* bits;
   const unsigned long long* status;  // look-back chain state (MT / fused: inclusive prefixes per block)
   const unsigned long long* woff;    // MC two-kernel form: exclusive (vertex, face) prefix of every generate block
@@ -446,6 +447,18 @@ struct GenArgs {
   long long* totals_a;
   long long* totals_b;
 };
+
+// Float64 field (MODE 3): everything is Float64 (src/marching_cubes.jl:100-104 with T = Float64).
+__device__ __forceinline__ void mc_interp_f64(const GenArgs& a, double va, double vb, const double pa[3], const double pb[3],
+                                              double out[3]) {
+  const double iso = a.iso_is_f32 ? (double)a.iso_f : a.iso_d;
+  const double mu = __ddiv_rn(__dsub_rn(iso, va), __dsub_rn(vb, va));
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const double d = a.p_is_f32 ? (double)__fsub_rn((float)pb[q], (float)pa[q]) : __dsub_rn(pb[q], pa[q]);
+    out[q] = __dadd_rn(pa[q], __dmul_rn(mu, d));
+  }
+}
 
 template <int MODE>
 __device__ __forceinline__ void mc_interp(const GenArgs& a, float va, float vb, const double pa[3], const double pb[3],
@@ -549,6 +562,15 @@ __device__ __forceinline__ void block_base(const GenArgs& a, unsigned b, unsigne
   bv = s_base[0], bf = s_base[1];
 }
 
+template <int MODE>
+struct FieldOf {
+  using type = float;
+};
+template <>
+struct FieldOf<3> {
+  using type = double;
+};
+
 // FUSED = false: generate after count_kernel (two-phase ABI: the caller sizes its arrays in between).
 // FUSED = true : classify-output -> mesh in ONE pass: count, decoupled look-back scan and generate fused
 //                (outputs must have capacity; totals are written by the last block).
@@ -562,7 +584,8 @@ mc_generate_kernel(GenArgs a, Grid g) {
   __shared__ uint32_t rec_yz[GEN_NB];
   __shared__ uint32_t rec_pk[GEN_NB];  // case | local vertex offset << 8 | local face offset << 20
   __shared__ uint8_t rec_c[GEN_NB];
-  __shared__ __align__(16) float corner[GEN_NB][8];
+  using T = typename FieldOf<MODE>::type;  // Float32, or Float64 for MODE 3
+  __shared__ __align__(16) T corner[GEN_NB][8];
   __shared__ uint8_t owner_v[GEN_MAXV], owner_f[GEN_MAXF];
   __shared__ uint8_t edge_c[12];
 
@@ -638,12 +661,12 @@ mc_generate_kernel(GenArgs a, Grid g) {
       const uint32_t rr = r0 + r;
       if (rr < cnt) {
         const uint32_t yz = rec_yz[rr];
-        const float* p = a.sdf + x + g.ldx * (long long)(yz & 0xffffu) + g.plane * (long long)(yz >> 16);
-        const float c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + g.ldx + 1), c3 = __ldg(p + g.ldx);
-        const float* p1 = p + g.plane;
-        const float c4 = __ldg(p1), c5 = __ldg(p1 + 1), c6 = __ldg(p1 + g.ldx + 1), c7 = __ldg(p1 + g.ldx);
-        *reinterpret_cast<float4*>(&corner[rr][0]) = make_float4(c0, c1, c2, c3);
-        *reinterpret_cast<float4*>(&corner[rr][4]) = make_float4(c4, c5, c6, c7);
+        const T* p = reinterpret_cast<const T*>(a.sdf) + x + g.ldx * (long long)(yz & 0xffffu) + g.plane * (long long)(yz >> 16);
+        const T c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + g.ldx + 1), c3 = __ldg(p + g.ldx);
+        const T* p1 = p + g.plane;
+        const T c4 = __ldg(p1), c5 = __ldg(p1 + 1), c6 = __ldg(p1 + g.ldx + 1), c7 = __ldg(p1 + g.ldx);
+        corner[rr][0] = c0, corner[rr][1] = c1, corner[rr][2] = c2, corner[rr][3] = c3;
+        corner[rr][4] = c4, corner[rr][5] = c5, corner[rr][6] = c6, corner[rr][7] = c7;
       }
     }
     uint32_t wtot;
@@ -681,7 +704,7 @@ mc_generate_kernel(GenArgs a, Grid g) {
       const uint32_t ca = cc & 15u, cb = cc >> 4;
       // MC corner offsets (dx | dy<<1 | dz<<2) for corners 0..7: 0,1,3,2,4,5,7,6
       const uint32_t oa = (0x67542310u >> (4 * ca)) & 7u, ob = (0x67542310u >> (4 * cb)) & 7u;
-      const float va = corner[s][ca], vb = corner[s][cb];
+      const T va = corner[s][ca], vb = corner[s][cb];
       const unsigned vy = yofs + (yz & 0xffffu), vz = zofs + (yz >> 16);
       double pa[3], pb[3];
       pa[0] = (oa & 1u) ? x1d : x0d;
@@ -693,7 +716,8 @@ mc_generate_kernel(GenArgs a, Grid g) {
       if (df & 2u) pb[1] = __ldg(a.coords + (vy + ((ob >> 1) & 1u)));
       if (df & 4u) pb[2] = __ldg(a.coords + (vz + (ob >> 2)));
       double p[3];
-      mc_interp<MODE>(a, va, vb, pa, pb, p);
+      if constexpr (MODE == 3) mc_interp_f64(a, va, vb, pa, pb, p);
+      else mc_interp<MODE>(a, va, vb, pa, pb, p);
       if (vfits || (long long)bv + k < a.vcap) {
         V* o = verts + 3 * ((long long)bv + k);
         o[0] = (V)p[0], o[1] = (V)p[1], o[2] = (V)p[2];

@@ -92,8 +92,8 @@ constexpr int MTG_MAXF = MTG_NB * 12;    // <= 12 faces per voxel
 constexpr int MTG_EDGES = 13;            // <= 13 crossed edges per voxel
 
 // A32: promote_type(typeof(iso), typeof(eps)) == Float32 (vertPos weights in Float32), else Float64.
-// P32: points (ranges) are Float32.  V: vertex element type.
-template <bool A32, bool P32, typename V>
+// P32: points (ranges) are Float32.  V: vertex element type.  T: field element type (Float64 implies !A32).
+template <bool A32, bool P32, typename V, typename T = float>
 #ifndef ISO_MT_MINB
 #define ISO_MT_MINB 8
 #endif
@@ -254,15 +254,29 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
       const uint32_t info = einfo_s[e];
       const int sx = info & 1, sy = (info >> 1) & 1, sz = (info >> 2) & 1;
       const int tx = (info >> 3) & 1, ty = (info >> 4) & 1, tz = (info >> 5) & 1;
-      const float srcVal = __ldg(a.sdf + (x + sx) + g.ldx * (vy + sy) + g.plane * (vz + sz));
-      const float tgtVal = __ldg(a.sdf + (x + tx) + g.ldx * (vy + ty) + g.plane * (vz + tz));
+      const T* fld = reinterpret_cast<const T*>(a.sdf);
+      const T srcVal = __ldg(fld + (x + sx) + g.ldx * (vy + sy) + g.plane * (vz + sz));
+      const T tgtVal = __ldg(fld + (x + tx) + g.ldx * (vy + ty) + g.plane * (vz + tz));
       const double bx = __ldg(xp + x), by = __ldg(yp + vy), bz = __ldg(zp + vz);
       const double ex = __ldg(xp + x + 1), ey = __ldg(yp + vy + 1), ez = __ldg(zp + vz + 1);
-      const float den = __fsub_rn(tgtVal, srcVal);
+      const T den = tgtVal - srcVal;  // one IEEE subtraction in the field type (-fmad=false, nothing to contract)
       double p[3];
       const double base[3] = {bx, by, bz}, endp[3] = {ex, ey, ez};
       const int c1[3] = {sx, sy, sz}, c2[3] = {tx, ty, tz};
-      if (A32) {
+      if constexpr (sizeof(T) == 8) {
+        // Float64 field: every operand promotes to Float64 (one(T) - eps too)
+        const double isod = a.iso_is_f32 ? (double)a.iso_f : a.iso_d;
+        const double q = __ddiv_rn(__dsub_rn(isod, (double)srcVal), (double)den);
+        const double epsd = a.eps_is_f32 ? (double)a.eps_f : a.eps_d;
+        const double av = jl_min(jl_max(q, epsd), __dsub_rn(1.0, epsd));
+        const double bw = __dsub_rn(1.0, av);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const double w = __dadd_rn(__dmul_rn((double)c1[d], bw), __dmul_rn((double)c2[d], av));
+          const double dd = P32 ? (double)__fsub_rn((float)endp[d], (float)base[d]) : __dsub_rn(endp[d], base[d]);
+          p[d] = __dadd_rn(base[d], __dmul_rn(w, dd));
+        }
+      } else if (A32) {
         const float q = __fdiv_rn(__fsub_rn(a.iso_f, srcVal), den);
         const float av = jl_min(jl_max(q, a.eps_f), __fsub_rn(1.0f, a.eps_f));
         const float bw = __fsub_rn(1.0f, av);
@@ -324,7 +338,10 @@ inline int launch_mt_generate(const GenArgs& a, const Grid& g, const b200iso_par
                               unsigned nb, cudaStream_t st) {
   const bool a32 = p.iso_is_f32 && p.eps_is_f32;
   const bool p32 = p.range_kind == B200ISO_RANGE_F32;
-  if (a32) {
+  if (p.field_is_f64) {
+    if (p32) mt_generate_kernel<false, true, double, double><<<nb, CB_THREADS, 0, st>>>(a, g, celloff);
+    else mt_generate_kernel<false, false, double, double><<<nb, CB_THREADS, 0, st>>>(a, g, celloff);
+  } else if (a32) {
     if (p32) mt_generate_kernel<true, true, float><<<nb, CB_THREADS, 0, st>>>(a, g, celloff);
     else if (vert_is_f64) mt_generate_kernel<true, false, double><<<nb, CB_THREADS, 0, st>>>(a, g, celloff);
     else mt_generate_kernel<true, false, float><<<nb, CB_THREADS, 0, st>>>(a, g, celloff);

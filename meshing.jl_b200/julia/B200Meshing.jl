@@ -12,7 +12,7 @@
 # the library on a B200.  Layout facts relied upon: Vector{NTuple{3,Float32}} == float[3n],
 # Vector{NTuple{3,Float64}} == double[3n], Vector{NTuple{3,Int}} == int64_t[3n] (isbits tuples are stored inline).
 #
-# There is no CPU fallback: anything but a dense Array{Float32,3} raises ArgumentError.
+# There is no CPU fallback: anything but a dense Array{Float32,3} / Array{Float64,3} raises ArgumentError.
 module B200Meshing
 
 export isosurface, MarchingCubes, MarchingTetrahedra
@@ -41,6 +41,8 @@ struct Params
     z0::Float64; z1::Float64
     x_offset::Int64
     nx_global::Int64
+    field_is_f64::Int32
+    reserved::Int32
 end
 
 const B200ISO_MC, B200ISO_MT = Int32(0), Int32(1)
@@ -74,7 +76,7 @@ range_kind(::Type{Float32}) = Int32(1)
 range_kind(::Type{Float64}) = Int32(2)
 range_kind(T) = throw(ArgumentError("unsupported range element type $T on the B200 path"))
 
-function params(method, X, Y, Z)
+function params(method, X, Y, Z, field_is_f64::Bool)
     kx, ky, kz = range_kind(typeof(first(X))), range_kind(typeof(first(Y))), range_kind(typeof(first(Z)))
     kx == ky == kz || throw(ArgumentError("X, Y, Z must share an element type on the B200 path"))
     iso, isf = scalar_kind(method.iso)
@@ -84,20 +86,20 @@ function params(method, X, Y, Z)
         algo = B200ISO_MT
         eps, epf = scalar_kind(method.eps)
     end
-    Params(algo, isf, epf, kx, iso, eps, first(X), last(X), first(Y), last(Y), first(Z), last(Z), 0, 0)
+    Params(algo, isf, epf, kx, iso, eps, first(X), last(X), first(Y), last(Y), first(Z), last(Z), 0, 0, Int32(field_is_f64), Int32(0))
 end
 
 vertex_eltype(p::Params) =
-    (p.iso_is_f32 == 0 || p.range_kind == 2 || (p.algo == B200ISO_MT && p.eps_is_f32 == 0)) ? Float64 : Float32
+    (p.field_is_f64 != 0 || p.iso_is_f32 == 0 || p.range_kind == 2 || (p.algo == B200ISO_MT && p.eps_is_f32 == 0)) ? Float64 : Float32
 
-function _isosurface(sdf::Array{Float32,3}, method, X, Y, Z)
+function _isosurface(sdf::Union{Array{Float32,3},Array{Float64,3}}, method, X, Y, Z)
     nx, ny, nz = size(sdf)
-    p = Ref(params(method, X, Y, Z))
+    p = Ref(params(method, X, Y, Z, eltype(sdf) === Float64))
     h = handle()
     nv, nf, f64 = Ref{Int64}(0), Ref{Int64}(0), Ref{Cint}(0)
     GC.@preserve sdf begin
         check(ccall((:b200iso_count, libb200iso), Cint,
-                    (Ptr{Cvoid}, Ref{Params}, Ptr{Float32}, Cint, Int64, Int64, Int64, Int64, Ref{Int64}, Ref{Int64}, Ref{Cint}),
+                    (Ptr{Cvoid}, Ref{Params}, Ptr{Cvoid}, Cint, Int64, Int64, Int64, Int64, Ref{Int64}, Ref{Int64}, Ref{Cint}),
                     h, p, pointer(sdf), B200ISO_HOST, nx, ny, nz, nx, nv, nf, f64))
     end
     VT = vertex_eltype(p[])
@@ -113,8 +115,8 @@ end
 
 # same positional signature and defaults as the reference
 function isosurface(sdf::AbstractArray{T,3}, method::Union{MarchingCubes,MarchingTetrahedra}, X=-1:1, Y=-1:1, Z=-1:1) where {T}
-    sdf isa Array{Float32,3} ||
-        throw(ArgumentError("the B200 path accepts a dense Array{Float32,3} (got $(typeof(sdf))); there is no CPU fallback"))
+    (sdf isa Array{Float32,3} || sdf isa Array{Float64,3}) ||
+        throw(ArgumentError("the B200 path accepts a dense Array{Float32,3} or Array{Float64,3} (got $(typeof(sdf))); there is no CPU fallback"))
     _isosurface(sdf, method, X, Y, Z)
 end
 # src/isosurface.jl:30-32

@@ -38,8 +38,10 @@ def test_argument_errors(pkg):
         api.make_params(api.MarchingCubes(iso="0"))
     with pytest.raises(TypeError):
         api.make_params(api.MarchingCubes(), (0, 1), (0.0, 1.0), (0, 1))
-    with pytest.raises(TypeError):  # non-Float32 field: outside the accelerated path, no CPU fallback
-        api.isosurface(np.zeros((4, 4, 4), np.float64))
+    with pytest.raises(TypeError):  # Integer / Float16 fields: outside the accelerated path, no CPU fallback
+        api.isosurface(np.zeros((4, 4, 4), np.int64))
+    with pytest.raises(TypeError):
+        api.isosurface(np.zeros((4, 4, 4), np.float16))
     with pytest.raises(TypeError):
         api.isosurface(np.zeros((4, 4), np.float32))
 

@@ -360,3 +360,49 @@ def test_full_size_1024_gyroid_properties(pkg, oracle):
         assert np.array_equal(gf, of)
         assert gv.shape == ov.shape and np.array_equal(gv[:, 1:], ov[:, 1:].astype(np.float32))
         assert np.abs(gv[:, 0].astype(np.float64) - ov[:, 0]).max() < 1e-6  # x: slab-local vs global LinRange rounding
+
+
+# ---- Float64 fields: the reference's own test inputs run through the CUDA path unchanged ----
+def test_reference_noisy_spheres_golden_counts_on_gpu(pkg, oracle):
+    """test/runtests.jl:152-172, the reference's only exact-count test, THROUGH THE CUDA PATH: Float64 field
+    (Float32 distances + Julia's MersenneTwister(0) noise), MarchingTetrahedra(iso=8.0): 3466 vertices, 6928 faces."""
+    import os
+    field = np.load(os.path.join(os.path.dirname(__file__), "golden", "noisy_spheres_input.npy"))
+    assert field.dtype == np.float64
+    points, faces = pkg.isosurface(field, pkg.MarchingTetrahedra(iso=8.0))
+    assert len(points) == 3466 and len(faces) == 6928 and points.dtype == np.float64
+    vo, fo = oracle.isosurface(field, oracle.MT, iso=8.0)
+    assert np.array_equal(faces, fo) and _bits_equal(points, vo)
+    pm, fm = pkg.isosurface(field, pkg.MarchingCubes(iso=8.0))
+    vo, fo = oracle.isosurface(field, oracle.MC, iso=8.0)
+    assert np.array_equal(fm, fo) and _bits_equal(pm, vo)
+
+
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+def test_reference_respect_origin_float64_on_gpu(pkg, oracle, algo):
+    """test/runtests.jl:127-149 with its own Float64 norm_sdf and iso = 0.5, through the CUDA path."""
+    g = np.arange(-100, 101) / 100.0
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    norm_sdf = np.asfortranarray(np.sqrt(X * X + Y * Y + Z * Z))
+    v, f = _check(pkg, oracle, norm_sdf, algo, iso=0.5, f32=False)
+    assert v.dtype == np.float64 and len(v) == (187800 if algo == "MC" else 140714)
+    assert np.allclose(v.mean(0), 0, atol=0.015)
+    assert np.allclose(v.max(0), 0.5, atol=1e-3) and np.allclose(v.min(0), -0.5, atol=1e-3)
+
+
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+@pytest.mark.parametrize("f32,rk", [(True, 0), (False, 0), (True, 1), (False, 2)])
+def test_float64_field_type_combinations(pkg, oracle, algo, f32, rk):
+    rng = np.random.default_rng(5)
+    s = np.asfortranarray(rng.standard_normal((23, 30, 41)))
+    _check(pkg, oracle, s, algo, iso=0.2, f32=f32, rk=rk, ranges=((-2, 3), (0, 1), (-7, -1)))
+    c = pkg.api.case_indices(s, _method(pkg, algo, 0.2, f32))
+    assert np.array_equal(c, oracle.case_indices(s, ALGOS[algo], iso=0.2, iso_is_f32=f32))
+
+
+def test_mixed_types_float64_vs_float32_on_gpu(pkg):
+    """test/runtests.jl:81-97: same face topology for a Float64 field and its Float32 copy (MT, ranges 0:1)."""
+    s = np.asfortranarray(np.random.default_rng(7).standard_normal((10, 10, 10)))
+    p1, f1 = pkg.isosurface(s, pkg.MarchingTetrahedra(), (0, 1), (0, 1), (0, 1))
+    p2, f2 = pkg.isosurface(s.astype(np.float32), pkg.MarchingTetrahedra(), (0, 1), (0, 1), (0, 1))
+    assert len(p1) == len(p2) and np.array_equal(f1, f2)
