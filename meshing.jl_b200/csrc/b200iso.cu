@@ -188,11 +188,6 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
     const bool tma_wanted = h->tma_mode == 1 || (h->tma_mode < 0 && ntasks >= 4096);
     if (vec && tma_wanted && iso::make_field_tmap(&tmap, sdf_f, nx, ny, nz, ldx)) {
       // TMA-staged classify: same tasks, cp.async.bulk.tensor boxes + per-warp mbarrier pipeline
-      static bool attr_set = false;
-      if (!attr_set) {
-        CU(cudaFuncSetAttribute(iso::signpack_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iso::TM_SMEM));
-        attr_set = true;
-      }
       const unsigned tb = (unsigned)((ntasks + iso::TM_WARPS - 1) / iso::TM_WARPS);
       iso::signpack_tma_kernel<<<tb, iso::TM_WARPS * 32, iso::TM_SMEM, st>>>(tmap, h->bits.p, g.nx, g.ny, g.nz, g.W, thr, nxseg, ntasks);
     } else if (vec)
@@ -299,6 +294,8 @@ int b200iso_create(b200iso_handle** out, int device) {
   b200iso_handle* h = new b200iso_handle();
   h->device = device;
   if (const char* e = getenv("B200ISO_TMA")) h->tma_mode = atoi(e) != 0 ? 1 : 0;
+  // per device: the TMA classify kernel needs more than the default 48 KB of dynamic shared memory
+  CU(cudaFuncSetAttribute(iso::signpack_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iso::TM_SMEM));
   CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
   CU(cudaMalloc((void**)&h->ticket, sizeof(unsigned int)));
@@ -311,7 +308,7 @@ int b200iso_create(b200iso_handle** out, int device) {
 int b200iso_destroy(b200iso_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  cudaDeviceSynchronize();  // (the caller's stream may already be gone: do not touch h->stream)
   h->bits.release(), h->celloff.release(), h->woff.release(), h->status.release(), h->coords.release(), h->field.release(), h->vstage.release(), h->fstage.release();
   if (h->ticket) cudaFree(h->ticket);
   if (h->totals_dev) cudaFree(h->totals_dev);
