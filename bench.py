@@ -14,7 +14,8 @@ A "step" is one full isosurface extraction (classify -> count+scan -> generate) 
 Workloads (config.workload):
   mc_gyroid   MarchingCubes(iso=0f0) on the Float32 gyroid; N GPUs hold an (n*N) x n x n volume split in
               x-slabs (x is the scan-outermost axis) -- weak scaling, n = 1024 (BASELINE configs[3])
-  mt_gyroid   MarchingTetrahedra(iso=0f0, eps=1f-3) on the 512^3 gyroid (configs[2]; replicas for N > 1)
+  mt_gyroid   MarchingTetrahedra(iso=0f0, eps=1f-3) on the 512^3 gyroid (configs[2]); N GPUs: (512*N) x 512 x 512 in
+              x-slabs with one ghost voxel row each
   mc_m2048    MarchingCubes on the multi-sphere/torus SDF, (256*N) x 2048 x 2048 (configs[4] at N = 8)
 --impl reference times the CPU restatement of the reference loops (oracle/, Julia is not installed) on the
 host cores, on a bounded x-range sample of the same field.
@@ -55,8 +56,9 @@ def workload_spec(name, n_override, world):
                          f"{n * world}x{n}x{n} samples on [0,4pi*{world}]x[0,4pi]^2, x-slabs of {n} voxel planes per GPU")
     if name == "mt_gyroid":
         n = n_override or 512
-        return dict(algo="MT", shape=(n, n, n), kind="gyroid", n=n, replicas=True,
-                    desc=f"MarchingTetrahedra(iso=0f0, eps=1f-3), Float32 gyroid {n}^3 on [0,4pi]^3 (one replica per GPU)")
+        return dict(algo="MT", shape=(n * world, n, n), kind="gyroid", n=n,
+                    desc=f"MarchingTetrahedra(iso=0f0, eps=1f-3), Float32 gyroid {n * world}x{n}x{n} samples on "
+                         f"[0,4pi*{world}]x[0,4pi]^2, x-slabs of {n} voxel planes per GPU (+1 ghost row)")
     n = n_override or 2048
     return dict(algo="MC", shape=(n // 8 * world, n, n), kind="mst", n=n,
                 desc=f"MarchingCubes(iso=0f0), multi-sphere/torus SDF (K=32, SplitMix64 seed 0x5EED2048), "
@@ -71,6 +73,8 @@ def slab_range(spec, rank, world):
     per = nxg // world
     xa = rank * per
     xb = nxg if rank == world - 1 else (rank + 1) * per + 1
+    if spec["algo"] == "MT" and rank > 0:
+        xa -= 1  # Marching Tetrahedra: the previous slab's last voxel row rides along as a ghost row
     return xa, xb
 
 
@@ -272,6 +276,7 @@ def main():
     params = pkg.api.make_params(method)
     if world > 1 and not spec.get("replicas"):
         params.x_offset, params.nx_global = xa, nxg  # slab vertices get the coordinates of the unsharded volume
+        params.x_ghost = int(spec["algo"] == "MT" and rank > 0)
     h = capi.Handle(local_rank)
     stream = torch.cuda.current_stream()
     h.set_stream(stream.cuda_stream)
@@ -325,7 +330,8 @@ def main():
     ms_step = float(t.item()) / args.steps
 
     # whole-job units
-    counts = torch.tensor([nv, nf, (nxl - 1) * (ny - 1) * (nz - 1)], dtype=torch.int64, device=device)
+    own_rows = nxl - 1 - int(params.x_ghost)
+    counts = torch.tensor([nv, nf, own_rows * (ny - 1) * (nz - 1)], dtype=torch.int64, device=device)
     if world > 1:
         dist.all_reduce(counts)
     tot_nv, tot_nf, tot_vox = [int(v) for v in counts.tolist()]

@@ -67,7 +67,13 @@ typedef struct b200iso_params {
    * points to doubles; vertices are Float64, promote_type(..., Float64)).  Integer / Float16 fields are not
    * accepted. */
   int32_t field_is_f64;
-  int32_t reserved;
+  /* Marching Tetrahedra x-slab sharding: 1 if the slab's first voxel row (samples x_offset, x_offset+1) is the
+   * GHOST row, i.e. the last voxel row of the previous slab.  MT vertices are shared between voxels and created by
+   * the owner voxel (the first one in scan order that touches the edge); faces of a slab's first own row reference
+   * vertices owned by that previous row.  The ghost row is counted (so those references resolve locally) but not
+   * emitted, totals exclude it, and face indices are vertex_base - ghost_vertices + local prefix -- so that the
+   * stitched slabs equal the unsharded mesh.  Every MT slab with x_offset > 0 carries one; 0 otherwise. */
+  int32_t x_ghost;
 } b200iso_params;
 
 /* ---- lifetime ------------------------------------------------------------------------------------ */

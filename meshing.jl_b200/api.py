@@ -178,7 +178,7 @@ def _isosurface_torch(t, params, device):
 
 
 def isosurface_slab(sdf_slab, method, x_offset, nx_global, vertex_base, *ranges, device=0):
-    """One rank's share of a sharded Marching Cubes call: `sdf_slab` holds samples [x_offset, x_offset+nx) of
+    """One rank's share of a sharded call (MC, or MT with its ghost row): `sdf_slab` holds samples [x_offset, x_offset+nx) of
     a volume with nx_global samples along x; `ranges` are X, Y, Z of the WHOLE volume.  Returns the slab's
     (vertices, faces) with `vertex_base` already added to the face indices.  Two-phase use
     (count -> all-gather -> generate) is `slab_count` + `slab_generate`."""
@@ -188,10 +188,10 @@ def isosurface_slab(sdf_slab, method, x_offset, nx_global, vertex_base, *ranges,
 
 def slab_count(sdf_slab, method, x_offset, nx_global, *ranges, device=0):
     """Phase 1 of a slab: classify + count.  numpy slab (host) or x-contiguous CUDA torch slab (device-resident)."""
-    if not isinstance(method, MarchingCubes):
-        raise TypeError("x-slab sharding is implemented for MarchingCubes (MT runs as replicas)")
     params = make_params(method, *ranges)
     params.x_offset, params.nx_global = x_offset, nx_global
+    # Marching Tetrahedra: every slab that does not start at x = 0 carries the previous slab's last voxel row
+    params.x_ghost = int(isinstance(method, MarchingTetrahedra) and x_offset > 0)
     if _is_torch(sdf_slab):
         import torch
         t = sdf_slab
@@ -204,11 +204,12 @@ def slab_count(sdf_slab, method, x_offset, nx_global, *ranges, device=0):
         h._slab_device = t.device
         return h, nv, nf, f64
     a = np.asfortranarray(np.asarray(sdf_slab))
-    if a.dtype != np.float32 or a.ndim != 3:
-        raise TypeError("3-D Float32 field expected")
+    if a.dtype not in (np.float32, np.float64) or a.ndim != 3:
+        raise TypeError("3-D Float32/Float64 field expected")
     nx, ny, nz = a.shape
     h = get_handle(device)
     h._slab_device = None
+    params.field_is_f64 = int(a.dtype == np.float64)
     nv, nf, f64 = h.count(params, a.ctypes.data, capi.HOST, nx, ny, nz, nx)
     return h, nv, nf, f64
 

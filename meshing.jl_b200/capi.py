@@ -23,7 +23,7 @@ class Params(ctypes.Structure):
                 ("range_kind", ctypes.c_int32), ("iso", ctypes.c_double), ("eps", ctypes.c_double),
                 ("x0", ctypes.c_double), ("x1", ctypes.c_double), ("y0", ctypes.c_double), ("y1", ctypes.c_double),
                 ("z0", ctypes.c_double), ("z1", ctypes.c_double), ("x_offset", ctypes.c_int64), ("nx_global", ctypes.c_int64),
-                ("field_is_f64", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("field_is_f64", ctypes.c_int32), ("x_ghost", ctypes.c_int32)]
 
 
 class B200IsoError(RuntimeError):

@@ -135,9 +135,11 @@ int check_params(const b200iso_params* p, int64_t nx, int64_t ny, int64_t nz, in
   if (nx < 0 || ny < 0 || nz < 0) return fail(B200ISO_EINVAL, "negative dimension");
   if (ldx < nx) return fail(B200ISO_EINVAL, "ldx (%lld) < nx (%lld)", (long long)ldx, (long long)nx);
   if (nx > 65536 || ny > 65536 || nz > 65536) return fail(B200ISO_EINVAL, "dimension larger than 65536 is not supported");
-  if (p->nx_global != 0 || p->x_offset != 0) {
-    if (p->algo != B200ISO_MC) return fail(B200ISO_EINVAL, "x-slab sharding is implemented for MarchingCubes only");
+  if (p->nx_global != 0 || p->x_offset != 0 || p->x_ghost != 0) {
     if (p->x_offset < 0 || p->nx_global < p->x_offset + nx) return fail(B200ISO_EINVAL, "slab [x_offset, x_offset+nx) outside nx_global");
+    if (p->x_ghost != 0 && p->x_ghost != 1) return fail(B200ISO_EINVAL, "x_ghost must be 0 or 1");
+    if (p->x_ghost && (p->algo != B200ISO_MT || p->x_offset == 0)) return fail(B200ISO_EINVAL, "x_ghost is for MT slabs that do not start at x = 0");
+    if (p->algo == B200ISO_MT && p->x_offset > 0 && !p->x_ghost) return fail(B200ISO_EINVAL, "an MT slab with x_offset > 0 needs its ghost row (x_ghost = 1)");
   }
   return 0;
 }
@@ -152,6 +154,8 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
   h->counted = false, h->totals_known = false;
   iso::Grid& g = h->grid;
   iso::grid_setup(g, nx, ny, nz, ldx);
+  g.xoff = (int)p->x_offset;
+  g.ghost = p->algo == B200ISO_MT && p->x_ghost != 0 ? 1 : 0;
   h->nblocks = (nx > 1 && ny > 1 && nz > 1) ? (long long)(nx - 1) * g.blocks_per_row : 0;
 
   if (h->nblocks == 0) {  // a dimension < 2: zero voxels, empty mesh (src/marching_cubes.jl:40)

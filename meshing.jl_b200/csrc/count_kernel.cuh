@@ -32,7 +32,7 @@ count_kernel(const uint32_t* __restrict__ bits, Grid g, unsigned long long* stat
   if (tm.live) {
     Quad q;
     if (load_quad(bits, g, tm.x, tm.y, tm.zq, q)) {
-      const int fxy = (tm.x == 0 ? 1 : 0) | (tm.y == 0 ? 2 : 0);
+      const int fxy = ((tm.x + g.xoff) == 0 ? 1 : 0) | (tm.y == 0 ? 2 : 0);  // low-boundary flags use GLOBAL x
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint32_t mm = active_mask(q, i);
@@ -73,8 +73,22 @@ count_kernel(const uint32_t* __restrict__ bits, Grid g, unsigned long long* stat
     unsigned long long ev, ef;
     lookback(status, (long long)b, av, af, ev, ef);
     if ((long long)b == nblocks - 1 && threadIdx.x == 0) {
-      totals_a[0] = (long long)(ev + av), totals_a[1] = (long long)(ef + af);
-      if (totals_b) totals_b[0] = (long long)(ev + av), totals_b[1] = (long long)(ef + af);
+      // a ghost row (MT sharding) is counted for the owner look-ups but belongs to the previous slab
+      unsigned long long gv = 0, gf = 0;
+      if (g.ghost) {
+        const long long gb = g.blocks_per_row - 1;  // last block of voxel row 0
+        if (gb == (long long)b) {
+          gv = ev + av, gf = ef + af;
+        } else {
+          unsigned long long sv, sf;
+          do {  // that block publishes its inclusive prefix as soon as its own look-back is done
+            sv = ld_relaxed(status + 2 * gb), sf = ld_relaxed(status + 2 * gb + 1);
+          } while ((sv >> 62) != 2 || (sf >> 62) != 2);
+          gv = sv & VAL_MASK, gf = sf & VAL_MASK;
+        }
+      }
+      totals_a[0] = (long long)(ev + av - gv), totals_a[1] = (long long)(ef + af - gf);
+      if (totals_b) totals_b[0] = totals_a[0], totals_b[1] = totals_a[1];
     }
   }
 }

@@ -43,6 +43,8 @@ struct Grid {
   long long row_words;   // ny * W : words between sample column (x,y) and (x+1,y)
   long long ldx;         // field leading dimension (elements)
   long long plane;       // ldx * ny
+  int xoff;              // global index of the slab's first sample plane (x-slab sharding; 0 otherwise)
+  int ghost;             // MT sharding: voxel row 0 belongs to the previous slab (counted, not emitted)
 };
 
 #ifndef ISO_CB_THREADS

@@ -131,6 +131,7 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
   const unsigned b = blockIdx.x;
   const TMap tm = thread_map(g, b);
   const int x = tm.x;
+  if (g.ghost && x == 0) return;  // ghost row of an MT slab: its faces and vertices belong to the previous slab
   // ---- A: active voxels per thread, exclusive scan (thread order == scan order) ----
   uint32_t tna;
   {
@@ -151,7 +152,13 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
   const double* yp = a.coords + g.nx;
   const double* zp = a.coords + g.nx + g.ny;
   V* verts = reinterpret_cast<V*>(a.verts);
-  const int fx = x == 0 ? 1 : 0;
+  const int fx = (x + g.xoff) == 0 ? 1 : 0;  // low-boundary flag in GLOBAL coordinates
+  // MT sharding: vertices/faces of the ghost row precede this slab's output; shift positions and ids by them
+  unsigned long long gshift_v = 0, gshift_f = 0;
+  if (g.ghost) {
+    gshift_v = a.status[2 * (unsigned long long)(g.blocks_per_row - 1)] & VAL_MASK;
+    gshift_f = a.status[2 * (unsigned long long)(g.blocks_per_row - 1) + 1] & VAL_MASK;
+  }
   uint32_t wv = 0;  // vertices of the block emitted by previous windows
 
   auto owned_word = [&](uint32_t c, int flags) -> unsigned long long {
@@ -215,7 +222,7 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
       } else {
         const int ox = x - (sh & 1), oy = vy - ((sh >> 1) & 1), oz = vz - (sh >> 2);
         const int eo = eshift_s[e * 8 + sh];  // the same edge in the owner's frame
-        const int oflags = (ox == 0 ? 1 : 0) | (oy == 0 ? 2 : 0) | (oz == 0 ? 4 : 0);
+        const int oflags = ((ox + g.xoff) == 0 ? 1 : 0) | (oy == 0 ? 2 : 0) | (oz == 0 ? 4 : 0);
         Quad q;
         load_cell(a.bits, g, ox, oy, oz >> 5, q);
         const int k = oz & 31;
@@ -239,8 +246,8 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
     }
     __syncthreads();
     const uint32_t nvr = wtot & 0xffffu, nfr = wtot >> 16;
-    const long long gv0 = (long long)bv + rv0;
-    const long long gf0 = (long long)bf;
+    const long long gv0 = (long long)bv + rv0 - (long long)gshift_v;  // position in this slab's vertex buffer
+    const long long gf0 = (long long)bf - (long long)gshift_f;
 
     // ---- B2: thread per vertex (vertPos, src/marching_tetrahedra.jl:42-55) ----
     for (uint32_t k = tid; k < nvr; k += CB_THREADS) {
@@ -325,7 +332,7 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
           const uint32_t slot = 3 * fi + j;
           const uint32_t e = (uint32_t)(faces_s[c * 3 + slot / 12] >> (5 * (slot % 12))) & 31u;
           const uint32_t es = __popc(cm & ((1u << (e - 1)) - 1u));
-          o[j] = vbase + (long long)bv + evid[s * MTG_EDGES + es] + 1;
+          o[j] = vbase - (long long)gshift_v + (long long)bv + evid[s * MTG_EDGES + es] + 1;
         }
       }
     }

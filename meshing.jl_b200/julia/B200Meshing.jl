@@ -42,7 +42,7 @@ struct Params
     x_offset::Int64
     nx_global::Int64
     field_is_f64::Int32
-    reserved::Int32
+    x_ghost::Int32
 end
 
 const B200ISO_MC, B200ISO_MT = Int32(0), Int32(1)

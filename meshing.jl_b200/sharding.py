@@ -5,18 +5,23 @@ contiguous range of the global vertex and face arrays.  A slab needs one halo sa
 exchange: the all-gather of (nverts_r, nfaces_r) -- 16 bytes per rank -- whose exclusive prefix is the
 vertex base added to the slab's face indices (b200iso_generate's vertex_base) and the offset of the slab in
 the stitched arrays.  Concatenating the slabs in rank order is byte-identical to the unsharded call.
-MT shards as replicas only (a slab's first voxel plane references vertices owned by the previous slab).
+MT shards the same way with one extra GHOST voxel row per slab (a slab's first own row references vertices owned by
+the previous slab's last row): the ghost row is counted locally, not emitted, and excluded from the totals.
 """
 import numpy as np
 
 
-def slab_bounds(nx, world, rank):
-    """Sample range [xa, xb) of rank `rank`: voxel planes [xa, xb-1); one halo plane except on the last rank.
-    Voxel planes are split as evenly as possible (nx-1 planes over `world` ranks)."""
+def slab_bounds(nx, world, rank, ghost=False):
+    """Sample range [xa, xb) of rank `rank`: voxel planes [xa, xb-1); one halo plane at high x.
+    Voxel planes are split as evenly as possible (nx-1 planes over `world` ranks).
+    ghost=True (Marching Tetrahedra): slabs that do not start at x = 0 additionally carry the previous slab's
+    last voxel row (one more sample plane at low x) -- b200iso_params.x_ghost."""
     nvx = max(nx - 1, 0)
     va = nvx * rank // world
     vb = nvx * (rank + 1) // world
-    return va, (vb + 1 if vb > va else va)
+    if vb <= va:
+        return va, va
+    return (va - 1 if ghost and va > 0 else va), vb + 1
 
 
 def exclusive_bases(counts, rank):

@@ -406,3 +406,30 @@ def test_mixed_types_float64_vs_float32_on_gpu(pkg):
     p1, f1 = pkg.isosurface(s, pkg.MarchingTetrahedra(), (0, 1), (0, 1), (0, 1))
     p2, f2 = pkg.isosurface(s.astype(np.float32), pkg.MarchingTetrahedra(), (0, 1), (0, 1), (0, 1))
     assert len(p1) == len(p2) and np.array_equal(f1, f2)
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+@pytest.mark.parametrize("kind", ["gyroid", "noise"])
+def test_sharded_mt_slabs_equal_unsharded(pkg, oracle, world, kind):
+    """Marching Tetrahedra x-slabs with a ghost voxel row: stitched == unsharded, byte for byte (shared vertices
+    across the slab boundary keep their global ids)."""
+    shape = (41, 19, 70)
+    s = getattr(pkg.synth, kind)(shape)
+    m = pkg.MarchingTetrahedra(iso=pkg.Float32(0.05), eps=pkg.Float32(1e-3))
+    X, Y, Z = (0, 3), (-1, 1), (2, 5)
+    v1, f1 = pkg.isosurface(s, m, X, Y, Z)
+    vo, fo = oracle.isosurface(s, 1, iso=0.05, iso_is_f32=True, eps_is_f32=True, ranges=(X, Y, Z))
+    assert np.array_equal(f1, fo) and _bits_equal(v1, vo)
+    counts, slabs = [], []
+    for r in range(world):
+        xa, xb = pkg.sharding.slab_bounds(shape[0], world, r, ghost=True)
+        slabs.append((xa, xb))
+        _, nv, nf, _ = pkg.api.slab_count(s[xa:xb], m, xa, shape[0], X, Y, Z)
+        counts.append((nv, nf))
+    assert sum(c[0] for c in counts) == len(v1) and sum(c[1] for c in counts) == len(f1)
+    parts = []
+    for r, (xa, xb) in enumerate(slabs):
+        vb, _ = pkg.sharding.exclusive_bases(counts, r)
+        parts.append(pkg.api.isosurface_slab(s[xa:xb], m, xa, shape[0], vb, X, Y, Z))
+    v, f = pkg.sharding.stitch(parts)
+    assert np.array_equal(f, f1) and _bits_equal(v, v1)
