@@ -245,6 +245,7 @@ int enqueue_generate(b200iso_handle* h, void* verts_dev, int64_t vcap, int64_t* 
     a.vbase_dev = (const long long*)vertex_base_dev, a.vbase = vertex_base;
     a.iso_d = p.iso, a.iso_f = (float)p.iso, a.eps_d = p.eps, a.eps_f = (float)p.eps;
     a.iso_is_f32 = p.iso_is_f32, a.eps_is_f32 = p.eps_is_f32, a.p_is_f32 = p.range_kind == B200ISO_RANGE_F32;
+    a.sdf_vec = !p.field_is_f64 && h->grid.ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(h->sdf_dev) & 15) == 0;
     a.ticket = h->ticket, a.nblocks = h->nblocks, a.totals_a = h->totals_dev, a.totals_b = h->totals_out;
     const unsigned nb = (unsigned)h->nblocks;
     const bool pf32 = p.range_kind == B200ISO_RANGE_F32;

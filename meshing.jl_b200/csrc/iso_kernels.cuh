@@ -443,6 +443,7 @@ struct GenArgs {
   float eps_f;
   double eps_d;
   int iso_is_f32, eps_is_f32, p_is_f32;  // typeof(iso), typeof(eps), eltype of the points (ranges)
+  int sdf_vec;                           // Float32 field, base 16-byte aligned, ldx % 4 == 0: aligned pair loads
   // fused single-pass kernels only: ticket counter, number of blocks, where the last block writes the totals
   unsigned int* ticket;
   long long nblocks;
@@ -564,6 +565,19 @@ __device__ __forceinline__ void block_base(const GenArgs& a, unsigned b, unsigne
   bv = s_base[0], bf = s_base[1];
 }
 
+// samples (x, x+1) of a row whose element x - (x & 3) is 16-byte aligned; ph = x & 3
+__device__ __forceinline__ void pair_load(const float* p, int ph, float2& out) {
+  if (ph == 0 || ph == 2) {
+    out = __ldg(reinterpret_cast<const float2*>(p));
+  } else if (ph == 1) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p - 1));
+    out = make_float2(v.y, v.z);
+  } else {
+    const float2 lo = __ldg(reinterpret_cast<const float2*>(p - 1)), hi = __ldg(reinterpret_cast<const float2*>(p + 1));
+    out = make_float2(lo.y, hi.x);
+  }
+}
+
 template <int MODE>
 struct FieldOf {
   using type = float;
@@ -664,9 +678,23 @@ mc_generate_kernel(GenArgs a, Grid g) {
       if (rr < cnt) {
         const uint32_t yz = rec_yz[rr];
         const T* p = reinterpret_cast<const T*>(a.sdf) + x + g.ldx * (long long)(yz & 0xffffu) + g.plane * (long long)(yz >> 16);
-        const T c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + g.ldx + 1), c3 = __ldg(p + g.ldx);
-        const T* p1 = p + g.plane;
-        const T c4 = __ldg(p1), c5 = __ldg(p1 + 1), c6 = __ldg(p1 + g.ldx + 1), c7 = __ldg(p1 + g.ldx);
+        T c0, c1, c2, c3, c4, c5, c6, c7;
+        if (sizeof(T) == 4 && a.sdf_vec) {
+          // Float32 field with 16-byte aligned rows: the (x, x+1) pair of each of the 4 rows comes from ONE aligned
+          // load (two when it straddles a 16-byte boundary) -- x is uniform over the block, no divergence.
+          // Fewer LSU sector accesses than 8 scalar gathers (the generate kernel is LSU-bound).
+          const float* r0 = reinterpret_cast<const float*>(p);
+          const float* r1 = r0 + g.ldx;
+          const float* r2 = r0 + g.plane;
+          const float* r3 = r2 + g.ldx;
+          float2 q0, q1, q2, q3;
+          pair_load(r0, x & 3, q0), pair_load(r1, x & 3, q1), pair_load(r2, x & 3, q2), pair_load(r3, x & 3, q3);
+          c0 = (T)q0.x, c1 = (T)q0.y, c3 = (T)q1.x, c2 = (T)q1.y, c4 = (T)q2.x, c5 = (T)q2.y, c7 = (T)q3.x, c6 = (T)q3.y;
+        } else {
+          c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + g.ldx + 1), c3 = __ldg(p + g.ldx);
+          const T* p1 = p + g.plane;
+          c4 = __ldg(p1), c5 = __ldg(p1 + 1), c6 = __ldg(p1 + g.ldx + 1), c7 = __ldg(p1 + g.ldx);
+        }
         corner[rr][0] = c0, corner[rr][1] = c1, corner[rr][2] = c2, corner[rr][3] = c3;
         corner[rr][4] = c4, corner[rr][5] = c5, corner[rr][6] = c6, corner[rr][7] = c7;
       }
