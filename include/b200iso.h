@@ -137,6 +137,24 @@ int b200iso_set_extract_mode(b200iso_handle* h, int mode);
 int b200iso_add_vertex_base_async(b200iso_handle* h, int64_t* faces_dev, int64_t fcap, const int64_t* totals_dev,
                                   const int64_t* vertex_base_dev);
 
+/* ---- one-shot host form (host arrays in, host arrays out, capacity known up front) ----------------------
+ * b200iso_extract_host: the whole isosurface() of a HOST field into caller-owned HOST arrays of capacity vcap
+ *                       vertices / fcap faces, as an x-slab software pipeline over three streams: strided H2D of
+ *                       slab k+1, the kernels of slab k and the D2H of slab k-1's mesh (straight into its final
+ *                       offset of verts/faces) overlap, so the call costs about the H2D time of the field instead
+ *                       of H2D + kernels + D2H (src/marching_cubes.jl:40 scans x outermost, so every x-slab's
+ *                       mesh is a contiguous piece of the output; MT slabs carry a ghost row).  Results are
+ *                       byte-identical to b200iso_count + b200iso_generate.  nverts/nfaces receive the true
+ *                       totals; if they exceed the capacities nothing useful is in the arrays and
+ *                       B200ISO_ECAPACITY is returned -- re-allocate and call again (vcap = fcap = 0 is a pure
+ *                       count).  Pinned (cudaHostAlloc / cudaHostRegister) arrays get the full PCIe rate;
+ *                       pageable ones work at the driver's staged-copy rate.  A rank's slab of a sharded volume
+ *                       (x_offset / nx_global / x_ghost set) is accepted; its face indices are slab-local
+ *                       (add the slab's vertex base afterwards).  Synchronous: the mesh is in the arrays on return. */
+int b200iso_extract_host(b200iso_handle* h, const b200iso_params* p, const void* sdf, int64_t nx, int64_t ny,
+                         int64_t nz, int64_t ldx, void* verts, int64_t vcap, int64_t* faces, int64_t fcap,
+                         int64_t* nverts, int64_t* nfaces, int* vert_is_f64);
+
 /* ---- parity / introspection ----------------------------------------------------------------------------
  * Per-voxel case index (_get_cubeindex, src/common.jl:10-20; corner order of the counted algo) for the
  * last counted field, (nx-1)(ny-1)(nz-1) bytes in scan-rank order ((x*(ny-1)+y)*(nz-1)+z). */

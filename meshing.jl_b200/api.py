@@ -115,7 +115,7 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
-def isosurface(sdf, *args, device=None):
+def isosurface(sdf, *args, device=None, capacity=None):
     """isosurface(sdf[, method][, X, Y, Z]) -> (vertices, faces)
 
     sdf      : 3-D Float32 (fast path) or Float64 array, `sdf[x, y, z]`.  numpy array (host; any strides, made x-contiguous like a
@@ -123,6 +123,8 @@ def isosurface(sdf, *args, device=None):
                tensors too and nothing crosses PCIe).
     method   : MarchingCubes(iso=...) (default) or MarchingTetrahedra(iso=..., eps=...)
     X, Y, Z  : ranges whose first/last elements give the extent; default -1:1 on every axis
+    capacity : optional (max_vertices, max_faces) guess for a host field: one-shot slab-pipelined call
+               (b200iso_extract_host) instead of count + generate; same result
     returns  : vertices (nverts, 3) Float32|Float64 by the reference's promotion rule, faces (nfaces, 3)
                int64, 1-based, in the reference's order (x-outermost, z-innermost voxel scan).
     """
@@ -145,11 +147,57 @@ def isosurface(sdf, *args, device=None):
     params.field_is_f64 = int(a.dtype == np.float64)
     nx, ny, nz = a.shape
     h = get_handle(0 if device is None else device)
+    if capacity is not None:
+        # one-shot slab pipeline (b200iso_extract_host): H2D, kernels and D2H overlap; exact re-run if the guess was short
+        f64 = _vert_is_f64(params)
+        vcap, fcap = int(capacity[0]), int(capacity[1])
+        for _ in range(2):
+            verts = np.empty((vcap, 3), dtype=np.float64 if f64 else np.float32)
+            faces = np.empty((fcap, 3), dtype=np.int64)
+            nv, nf, f64, fits = h.extract_host(params, a.ctypes.data, nx, ny, nz, nx, verts.ctypes.data, vcap, faces.ctypes.data, fcap)
+            if fits:
+                return verts[:nv], faces[:nf]
+            vcap, fcap = nv, nf
+        raise RuntimeError("b200iso_extract_host: capacity still too small after an exact re-run")
     nv, nf, f64 = h.count(params, a.ctypes.data, capi.HOST, nx, ny, nz, nx)
     verts = np.empty((nv, 3), dtype=np.float64 if f64 else np.float32)
     faces = np.empty((nf, 3), dtype=np.int64)
     h.generate(verts.ctypes.data, faces.ctypes.data, capi.HOST, 0)
     return verts, faces
+
+
+def _vert_is_f64(params):
+    """float(promote_type(eltype(X), eltype(Y), eltype(Z), T_sdf, typeof(iso)[, typeof(eps)])) == Float64
+    (src/marching_cubes.jl:31, src/marching_tetrahedra.jl:131)."""
+    return bool(params.field_is_f64 or not params.iso_is_f32 or params.range_kind == 2
+                or (params.algo == 1 and not params.eps_is_f32))
+
+
+def isosurface_into(sdf, verts_out, faces_out, *args, device=None):
+    """isosurface() of a host field into caller-owned host arrays (e.g. pinned, re-used every time step) through the
+    one-shot slab pipeline b200iso_extract_host.  verts_out: (vcap, 3) float32|float64 C-contiguous, faces_out:
+    (fcap, 3) int64.  Returns (nverts, nfaces); raises B200IsoError(ECAPACITY) if the mesh does not fit."""
+    if args and isinstance(args[0], (MarchingCubes, MarchingTetrahedra)):
+        method, rest = args[0], args[1:]
+    else:
+        method, rest = MarchingCubes(), args
+    params = make_params(method, *rest)
+    a = np.asarray(sdf)
+    if a.ndim != 3 or a.dtype not in (np.float32, np.float64):
+        raise TypeError("3-D Float32/Float64 field expected")
+    if not a.flags.f_contiguous:
+        raise TypeError("isosurface_into takes a Fortran-ordered (x-contiguous) field: it does not copy")
+    params.field_is_f64 = int(a.dtype == np.float64)
+    want = np.float64 if _vert_is_f64(params) else np.float32
+    if verts_out.dtype != want or faces_out.dtype != np.int64 or not verts_out.flags.c_contiguous or not faces_out.flags.c_contiguous:
+        raise TypeError(f"verts_out must be C-contiguous {np.dtype(want)} (n, 3), faces_out C-contiguous int64 (n, 3)")
+    nx, ny, nz = a.shape
+    h = get_handle(0 if device is None else device)
+    nv, nf, _, fits = h.extract_host(params, a.ctypes.data, nx, ny, nz, nx, verts_out.ctypes.data, verts_out.shape[0],
+                                     faces_out.ctypes.data, faces_out.shape[0])
+    if not fits:
+        raise capi.B200IsoError(capi.ECAPACITY, f"mesh has {nv} vertices / {nf} faces; capacity {verts_out.shape[0]} / {faces_out.shape[0]}")
+    return nv, nf
 
 
 def _isosurface_torch(t, params, device):

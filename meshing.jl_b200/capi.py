@@ -14,6 +14,7 @@ HEADER = os.path.join(ROOT, "include", "b200iso.h")
 
 MC, MT = 0, 1
 HOST, DEVICE = 0, 1
+ECAPACITY = -5  # B200ISO_ECAPACITY
 RANGE_INT, RANGE_F32, RANGE_F64 = 0, 1, 2
 
 
@@ -71,6 +72,7 @@ def load():
     L.b200iso_generate_async.argtypes = [vp, vp, i64, vp, i64, vp, i64]
     L.b200iso_totals.argtypes = [vp, pi64, pi64, pci]
     L.b200iso_extract_async.argtypes = [vp, pp, vp, i64, i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]
+    L.b200iso_extract_host.argtypes = [vp, pp, vp, i64, i64, i64, i64, vp, i64, vp, i64, pi64, pi64, pci]
     L.b200iso_add_vertex_base_async.argtypes = [vp, vp, i64, vp, vp]
     L.b200iso_set_extract_mode.argtypes = [vp, ci]
     L.b200iso_case_indices.argtypes = [vp, vp, ci]
@@ -138,6 +140,17 @@ class Handle:
                                             ctypes.c_void_p(verts_dev_ptr), vcap, ctypes.c_void_p(faces_dev_ptr), fcap,
                                             ctypes.c_void_p(vertex_base_dev_ptr or 0), vertex_base,
                                             ctypes.c_void_p(totals_dev_ptr or 0)))
+
+    def extract_host(self, params, sdf_ptr, nx, ny, nz, ldx, verts_ptr, vcap, faces_ptr, fcap):
+        """One-shot slab-pipelined host call.  Returns (nverts, nfaces, vert_is_f64, fits); fits=False means the
+        capacities were too small (B200ISO_ECAPACITY) and the totals say what to allocate."""
+        nv, nf, f64 = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()
+        rc = self.L.b200iso_extract_host(self.h, ctypes.byref(params), ctypes.c_void_p(sdf_ptr), nx, ny, nz, ldx,
+                                         ctypes.c_void_p(verts_ptr or 0), vcap, ctypes.c_void_p(faces_ptr or 0), fcap,
+                                         ctypes.byref(nv), ctypes.byref(nf), ctypes.byref(f64))
+        if rc != ECAPACITY:
+            _check(rc)
+        return nv.value, nf.value, bool(f64.value), rc == 0
 
     def set_extract_mode(self, mode):
         """0 = count then generate (default), 1 = fused single-pass kernel"""

@@ -5,7 +5,11 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
+#include <atomic>
+#include <thread>
+#include <vector>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -16,6 +20,7 @@
 #include "mt_kernels.cuh"
 #include "count_kernel.cuh"
 #include "signpack_tma.cuh"
+#include "host_pipeline.h"
 
 namespace {
 
@@ -83,6 +88,10 @@ struct b200iso_handle {
   DevBuf<unsigned char> field;   // staging of a host field
   DevBuf<unsigned char> vstage;  // staging of vertices for host output
   DevBuf<long long> fstage;
+  DevBuf<unsigned char> vstage1;  // second staging set: the slab pipeline of b200iso_extract_host ping-pongs
+  DevBuf<long long> fstage1;
+  hostpipe::Pool pool;             // copy lanes (streams, pinned chunks, events) of the HOST paths
+  std::vector<cudaEvent_t> slab_ev;  // b200iso_extract_host: slab k generated; [n-2] fork, [n-1] join
   unsigned int* ticket = nullptr;
   long long* totals_dev = nullptr;   // device int64[2]
   long long* totals_host = nullptr;  // pinned int64[2]
@@ -298,6 +307,7 @@ int b200iso_create(b200iso_handle** out, int device) {
   CU(cudaSetDevice(device));
   b200iso_handle* h = new b200iso_handle();
   h->device = device;
+  h->pool.device = device;
   if (const char* e = getenv("B200ISO_TMA")) h->tma_mode = atoi(e) != 0 ? 1 : 0;
   // per device: the TMA classify kernel needs more than the default 48 KB of dynamic shared memory
   CU(cudaFuncSetAttribute(iso::signpack_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iso::TM_SMEM));
@@ -314,6 +324,9 @@ int b200iso_destroy(b200iso_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();  // (the caller's stream may already be gone: do not touch h->stream)
+  h->vstage1.release(), h->fstage1.release();
+  for (cudaEvent_t e : h->slab_ev) cudaEventDestroy(e);
+  h->pool.release();
   h->bits.release(), h->celloff.release(), h->woff.release(), h->status.release(), h->coords.release(), h->field.release(), h->vstage.release(), h->fstage.release();
   if (h->ticket) cudaFree(h->ticket);
   if (h->totals_dev) cudaFree(h->totals_dev);
@@ -412,7 +425,20 @@ int b200iso_count(b200iso_handle* h, const b200iso_params* p, const void* sdf, i
     if (int rc = h->field.reserve((size_t)dldx * ny * nz * esz)) return rc;
     h->begin_step();
     if (int rc = h->rec(b200iso_handle::E_H0)) return rc;
-    if (dldx == ldx)
+    if (!hostpipe::is_pinned(sdf)) {
+      // pageable caller array (the usual Julia Array): worker threads stage it through pinned chunks
+      if (h->slab_ev.empty()) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->slab_ev.push_back(e);
+      }
+      CU(cudaEventRecord(h->slab_ev[0], h->stream));
+      hostpipe::Slab whole;
+      whole.dst = h->field.p, whole.dpitch = (size_t)dldx * esz, whole.x0 = 0, whole.x1 = nx;
+      hostpipe::Uploader up;
+      CU(up.start(&h->pool, {whole}, (const unsigned char*)sdf, (size_t)ldx * esz, esz, (size_t)ny * nz, h->slab_ev[0]));
+      CU(up.wait_slab(0, h->stream));
+    } else if (dldx == ldx)
       CU(cudaMemcpyAsync(h->field.p, sdf, (size_t)ldx * ny * nz * esz, cudaMemcpyHostToDevice, h->stream));
     else
       CU(cudaMemcpy2DAsync(h->field.p, (size_t)dldx * esz, sdf, (size_t)ldx * esz, (size_t)nx * esz,
@@ -443,11 +469,143 @@ int b200iso_generate(b200iso_handle* h, void* verts, int64_t* faces, int mem, in
     if (int rc = h->fstage.reserve((size_t)h->nfaces * 3 + 2)) return rc;
     if (int rc = enqueue_generate(h, h->vstage.p, h->nverts, (int64_t*)h->fstage.p, h->nfaces, nullptr, vertex_base)) return rc;
     if (int rc = h->rec(b200iso_handle::E_D0)) return rc;
-    if (h->nverts) CU(cudaMemcpyAsync(verts, h->vstage.p, (size_t)h->nverts * 3 * vsz, cudaMemcpyDeviceToHost, h->stream));
-    if (h->nfaces) CU(cudaMemcpyAsync(faces, h->fstage.p, (size_t)h->nfaces * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (!(hostpipe::is_pinned(verts) && hostpipe::is_pinned(faces)) && (h->nverts || h->nfaces)) {
+      // pageable caller arrays: worker threads drain the staging through pinned chunks
+      if (h->slab_ev.empty()) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->slab_ev.push_back(e);
+      }
+      CU(cudaEventRecord(h->slab_ev[0], h->stream));
+      hostpipe::Downloader down;
+      CU(down.start(&h->pool, 1, false, h->slab_ev[0]));
+      hostpipe::Downloader::Job j;
+      j.src[0] = h->vstage.p, j.dst[0] = (unsigned char*)verts, j.bytes[0] = (size_t)h->nverts * 3 * vsz;
+      j.src[1] = (const unsigned char*)h->fstage.p, j.dst[1] = (unsigned char*)faces, j.bytes[1] = (size_t)h->nfaces * 3 * sizeof(int64_t);
+      j.ready = h->slab_ev[0];
+      CU(down.push(0, j));
+      CU(down.finish());
+    } else {
+      if (h->nverts) CU(cudaMemcpyAsync(verts, h->vstage.p, (size_t)h->nverts * 3 * vsz, cudaMemcpyDeviceToHost, h->stream));
+      if (h->nfaces) CU(cudaMemcpyAsync(faces, h->fstage.p, (size_t)h->nfaces * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    }
     if (int rc = h->rec(b200iso_handle::E_D1)) return rc;
     CU(cudaStreamSynchronize(h->stream));
   }
+  return 0;
+}
+
+// One-shot host form: x-slab software pipeline over three streams.  x is the scan-outermost
+// axis, so the mesh of voxel rows [a, b) is a contiguous piece of the output and needs sample planes [a, b] only:
+//   in_stream : strided (2-D) H2D copies of the slabs, all enqueued up front (>= 256 B rows run at full PCIe rate)
+//   h->stream : per slab classify -> count/scan -> (16-byte totals read-back) -> generate into a staging set
+//   out_stream: D2H of slab k's vertices/faces straight into their final offsets of the caller's arrays,
+//               overlapping the H2D of the slabs behind it (PCIe is full duplex)
+// Every slab is the sharded sub-problem of api.isosurface_slab (x_offset / nx_global / vertex base; Marching
+// Tetrahedra slabs carry their ghost row), so the concatenation is byte-identical to the unsharded mesh.
+int b200iso_extract_host(b200iso_handle* h, const b200iso_params* p, const void* sdf, int64_t nx, int64_t ny, int64_t nz,
+                         int64_t ldx, void* verts, int64_t vcap, int64_t* faces, int64_t fcap, int64_t* nverts,
+                         int64_t* nfaces, int* vert_is_f64) {
+  if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  if (int rc = check_params(p, nx, ny, nz, ldx)) return rc;
+  if (!sdf && nx * ny * nz > 0) return fail(B200ISO_EINVAL, "sdf is NULL");
+  if (vcap < 0 || fcap < 0) return fail(B200ISO_EINVAL, "negative capacity");
+  if ((vcap > 0 && !verts) || (fcap > 0 && !faces)) return fail(B200ISO_EINVAL, "output pointer is NULL");
+  CU(cudaSetDevice(h->device));
+  const int f64 = vertex_is_f64(*p);
+  if (vert_is_f64) *vert_is_f64 = f64;
+  if (nverts) *nverts = 0;
+  if (nfaces) *nfaces = 0;
+  if (nx < 2 || ny < 2 || nz < 2) return 0;  // zero voxels, empty mesh
+  const size_t esz = p->field_is_f64 ? 8 : 4, vsz = f64 ? 8 : 4;
+  const bool mt = p->algo == B200ISO_MT;
+  // slabs of >= 256 samples, at most 8, and only on big fields.  Measured at 1024^3 (pinned arrays, PCIe 5 x16):
+  // 4 slabs 88.4 ms, 8 slabs 90.9, 16 slabs 98.8, 32 slabs 158 -- against 96.3 ms for count + generate; alone the
+  // strided copies hold 55.6 GB/s down to 256-byte rows, but next to the D2H traffic the narrow ones fall behind.
+  const int64_t nvx = nx - 1;
+  int S = (size_t)nx * ny * nz * esz < ((size_t)32 << 20) ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(8, nx / 256));
+  if (const char* e = getenv("B200ISO_HOST_SLABS")) S = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(64, nvx), atoi(e)));
+  // voxel-row boundaries; the first sample of every slab (its ghost row for MT) is 16-byte aligned in the staging
+  std::vector<int64_t> bound(S + 1);
+  for (int k = 0; k <= S; ++k) {
+    int64_t b = nvx * k / S;
+    if (k > 0 && k < S) b = std::min(nvx, b / 4 * 4 + (mt ? 1 : 0));
+    bound[k] = b;
+  }
+  for (int k = 1; k <= S; ++k) bound[k] = std::max(bound[k], bound[k - 1]);
+  while (h->slab_ev.size() < (size_t)S + 2) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->slab_ev.push_back(e);
+  }
+  // device staging: every slab compact (row pitch = its padded width), holding sample planes [a - lo, b]
+  std::vector<hostpipe::Slab> slabs(S);
+  size_t field_bytes = 0;
+  for (int k = 0; k < S; ++k) {
+    const int64_t a = bound[k], b = bound[k + 1];
+    const int lo = a > 0 && mt ? 1 : 0;  // an MT slab starts with its ghost row
+    hostpipe::Slab& sb = slabs[k];
+    sb.x0 = a - lo, sb.x1 = b > a ? b + 1 : sb.x0;
+    sb.dpitch = (size_t)((sb.x1 - sb.x0 + 3) / 4 * 4) * esz;
+    field_bytes = (field_bytes + 255) / 256 * 256;
+    sb.dst = (unsigned char*)field_bytes;  // offset for now
+    field_bytes += sb.dpitch * (size_t)ny * nz;
+  }
+  if (int rc = h->field.reserve(field_bytes)) return rc;
+  for (hostpipe::Slab& sb : slabs) sb.dst = h->field.p + (size_t)sb.dst;
+  cudaStream_t st = h->stream;
+  const cudaEvent_t ev_fork = h->slab_ev[S];
+  h->begin_step();
+  if (int rc = h->rec(b200iso_handle::E_H0)) return rc;
+  CU(cudaEventRecord(ev_fork, st));  // the copy lanes start after whatever the caller's stream holds
+  // (1) H2D, enqueued by the uploader's worker threads (the enqueue of a million-row 2-D copy keeps its thread busy
+  // for about the copy's duration, and this thread has the kernels and the D2H of the earlier slabs to enqueue).
+  hostpipe::Uploader up;
+  hostpipe::Downloader down;
+  CU(up.start(&h->pool, slabs, (const unsigned char*)sdf, (size_t)ldx * esz, esz, (size_t)ny * nz, ev_fork));
+  CU(down.start(&h->pool, S, hostpipe::is_pinned(verts) && hostpipe::is_pinned(faces), ev_fork));
+  // (2) per slab: count, totals, generate into staging set (job & 1), D2H into the final offsets
+  int64_t cv = 0, cf = 0;
+  int njobs = 0;
+  bool overflow = false;
+  for (int k = 0; k < S; ++k) {
+    const int64_t a = bound[k], b = bound[k + 1];
+    if (b <= a) continue;
+    // (a caller's own slab of a sharded volume keeps its x_offset / nx_global / ghost row: sub-slab 0 inherits them)
+    const int ghost = a > 0 ? (mt ? 1 : 0) : p->x_ghost;
+    b200iso_params pk = *p;
+    pk.x_offset = p->x_offset + a - (a > 0 ? ghost : 0), pk.nx_global = p->nx_global > 0 ? p->nx_global : nx, pk.x_ghost = ghost;
+    const int lo = a > 0 ? ghost : 0;  // sample planes below voxel row a that the sub-slab starts with
+    CU(up.wait_slab(k, st));
+    if (k == S - 1)
+      if (int rc = h->rec(b200iso_handle::E_H1)) return rc;
+    if (int rc = enqueue_count(h, &pk, slabs[k].dst, b - a + 1 + lo, ny, nz, (int64_t)(slabs[k].dpitch / esz), nullptr, true)) return rc;
+    if (int rc = fetch_totals(h)) return rc;
+    const int64_t nv = h->nverts, nf = h->nfaces;
+    if (cv + nv > vcap || cf + nf > fcap) overflow = true;
+    if (!overflow && (nv > 0 || nf > 0)) {
+      DevBuf<unsigned char>& vs = (njobs & 1) ? h->vstage1 : h->vstage;
+      DevBuf<long long>& fs = (njobs & 1) ? h->fstage1 : h->fstage;
+      if (njobs >= 2) CU(down.wait_job(njobs - 2));  // this staging set's previous D2H
+      if (int rc = vs.reserve((size_t)nv * 3 * vsz + 16)) return rc;
+      if (int rc = fs.reserve((size_t)nf * 3 + 2)) return rc;
+      if (int rc = enqueue_generate(h, vs.p, nv, (int64_t*)fs.p, nf, nullptr, cv)) return rc;
+      CU(cudaEventRecord(h->slab_ev[k], st));
+      hostpipe::Downloader::Job j;
+      j.src[0] = vs.p, j.dst[0] = (unsigned char*)verts + (size_t)cv * 3 * vsz, j.bytes[0] = (size_t)nv * 3 * vsz;
+      j.src[1] = (const unsigned char*)fs.p, j.dst[1] = (unsigned char*)(faces + (size_t)cf * 3), j.bytes[1] = (size_t)nf * 3 * sizeof(int64_t);
+      j.ready = h->slab_ev[k];
+      CU(down.push(njobs++, j));
+    }
+    cv += nv, cf += nf;
+  }
+  up.join();
+  CU(down.finish());  // the mesh is in the caller's arrays
+  CU(cudaStreamSynchronize(st));
+  h->counted = false;  // the handle holds the last slab only: not a state b200iso_generate may continue from
+  if (nverts) *nverts = cv;
+  if (nfaces) *nfaces = cf;
+  if (overflow) return fail(B200ISO_ECAPACITY, "mesh has %lld vertices / %lld faces, capacity is %lld / %lld", (long long)cv, (long long)cf, (long long)vcap, (long long)fcap);
   return 0;
 }
 

@@ -16,6 +16,7 @@
 module B200Meshing
 
 export isosurface, MarchingCubes, MarchingTetrahedra
+# (B200Meshing.isosurface_sized is the one-shot host form; not exported, the reference has no such name)
 
 const libb200iso = get(ENV, "B200ISO_LIB", joinpath(@__DIR__, "..", "lib", "libb200iso.so"))
 
@@ -47,6 +48,7 @@ end
 
 const B200ISO_MC, B200ISO_MT = Int32(0), Int32(1)
 const B200ISO_HOST, B200ISO_DEVICE = Cint(0), Cint(1)
+const B200ISO_ECAPACITY = Cint(-5)
 
 last_error() = unsafe_string(ccall((:b200iso_last_error, libb200iso), Cstring, ()))
 check(rc) = rc == 0 ? nothing : error("b200iso error $rc: $(last_error())")
@@ -111,6 +113,30 @@ function _isosurface(sdf::Union{Array{Float32,3},Array{Float64,3}}, method, X, Y
                     h, pointer(vts), pointer(fcs), B200ISO_HOST, 0))
     end
     vts, fcs
+end
+
+# One-shot form for callers that can guess (or remember) the mesh size: b200iso_extract_host pipelines H2D, kernels
+# and D2H over x-slabs.  `capacity` = (max vertices, max faces); a short guess costs one exact re-run.
+function isosurface_sized(sdf::Union{Array{Float32,3},Array{Float64,3}}, method::Union{MarchingCubes,MarchingTetrahedra},
+                          X=-1:1, Y=-1:1, Z=-1:1; capacity::NTuple{2,Int})
+    nx, ny, nz = size(sdf)
+    p = Ref(params(method, X, Y, Z, eltype(sdf) === Float64))
+    h = handle()
+    VT = vertex_eltype(p[])
+    nv, nf, f64 = Ref{Int64}(0), Ref{Int64}(0), Ref{Cint}(0)
+    vcap, fcap = capacity
+    for _ in 1:2
+        vts = Vector{NTuple{3,VT}}(undef, vcap)
+        fcs = Vector{NTuple{3,Int}}(undef, fcap)
+        rc = GC.@preserve sdf vts fcs ccall((:b200iso_extract_host, libb200iso), Cint,
+            (Ptr{Cvoid}, Ref{Params}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Int64}, Int64,
+             Ref{Int64}, Ref{Int64}, Ref{Cint}),
+            h, p, pointer(sdf), nx, ny, nz, nx, pointer(vts), vcap, pointer(fcs), fcap, nv, nf, f64)
+        rc == 0 && return resize!(vts, nv[]), resize!(fcs, nf[])
+        rc == B200ISO_ECAPACITY || check(rc)
+        vcap, fcap = nv[], nf[]
+    end
+    error("b200iso_extract_host: capacity still too small after an exact re-run")
 end
 
 # same positional signature and defaults as the reference

@@ -433,3 +433,115 @@ def test_sharded_mt_slabs_equal_unsharded(pkg, oracle, world, kind):
         parts.append(pkg.api.isosurface_slab(s[xa:xb], m, xa, shape[0], vb, X, Y, Z))
     v, f = pkg.sharding.stitch(parts)
     assert np.array_equal(f, f1) and _bits_equal(v, v1)
+
+
+# ---- one-shot host form: b200iso_extract_host (x-slab pipelined H2D || kernels || D2H) -------------------------
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+@pytest.mark.parametrize("shape,kind,slabs", [((70, 33, 41), "gyroid", 1), ((70, 33, 41), "gyroid", 3), ((70, 33, 41), "noise", 7),
+                                              ((131, 20, 37), "sphere", 16), ((9, 12, 300), "noise", 64), ((2, 9, 9), "noise", 5)])
+def test_extract_host_equals_two_phase(pkg, oracle, monkeypatch, algo, shape, kind, slabs):
+    """Every slab count gives the bytes of count + generate, which the tests above pin to the oracle."""
+    s = getattr(pkg.synth, kind)(shape)
+    m = _method(pkg, algo, 0.0, True)
+    v0, f0 = pkg.isosurface(s, m, (0, 2), (-1, 1), (3, 4))
+    monkeypatch.setenv("B200ISO_HOST_SLABS", str(slabs))
+    v1, f1 = pkg.isosurface(s, m, (0, 2), (-1, 1), (3, 4), capacity=(len(v0) + 5, len(f0) + 3))
+    assert np.array_equal(f1, f0) and _bits_equal(v1, v0)
+    vo, fo = oracle.isosurface(s, ALGOS[algo], iso=0.0, iso_is_f32=True, eps_is_f32=True, ranges=((0, 2), (-1, 1), (3, 4)))
+    assert np.array_equal(f1, fo) and _bits_equal(v1, vo)
+
+
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+def test_extract_host_natural_slabs_and_types(pkg, oracle, algo):
+    """A field big enough (> 32 MB) for the default slab split; Float64 method => Float64 vertices; Float64 field."""
+    s = pkg.synth.gyroid((530, 130, 140))
+    for f32 in (True, False):
+        m = _method(pkg, algo, 0.05, f32)
+        v0, f0 = pkg.isosurface(s, m)
+        v1, f1 = pkg.isosurface(s, m, capacity=(len(v0), len(f0)))
+        assert v1.dtype == (np.float32 if f32 else np.float64)
+        assert np.array_equal(f1, f0) and _bits_equal(v1, v0)
+    s64 = pkg.synth.gyroid((150, 190, 160)).astype(np.float64) * 1.000000001
+    m = _method(pkg, algo, 0.0, False)
+    v0, f0 = pkg.isosurface(s64, m)
+    v1, f1 = pkg.isosurface(s64, m, capacity=(len(v0), len(f0)))
+    assert np.array_equal(f1, f0) and _bits_equal(v1, v0)
+
+
+def test_extract_host_capacity_protocol(pkg, monkeypatch):
+    """Too small => B200ISO_ECAPACITY with the true totals; vcap = fcap = 0 is a pure count; isosurface(capacity=)
+    re-runs exactly; isosurface_into writes into caller arrays."""
+    s = pkg.synth.gyroid((90, 40, 40))
+    m = pkg.MarchingCubes(iso=pkg.Float32(0))
+    v0, f0 = pkg.isosurface(s, m)
+    monkeypatch.setenv("B200ISO_HOST_SLABS", "4")
+    h = pkg.api.get_handle(0)
+    p = pkg.api.make_params(m)
+    a = np.asfortranarray(s)
+    nv, nf, f64, fits = h.extract_host(p, a.ctypes.data, *a.shape, a.shape[0], 0, 0, 0, 0)
+    assert (nv, nf, f64, fits) == (len(v0), len(f0), False, False)
+    vb, fb = np.empty((nv // 2, 3), np.float32), np.empty((nf, 3), np.int64)
+    nv2, nf2, _, fits = h.extract_host(p, a.ctypes.data, *a.shape, a.shape[0], vb.ctypes.data, len(vb), fb.ctypes.data, len(fb))
+    assert (nv2, nf2, fits) == (nv, nf, False)
+    v1, f1 = pkg.isosurface(s, m, capacity=(10, 10))
+    assert np.array_equal(f1, f0) and _bits_equal(v1, v0)
+    vb, fb = np.full((nv + 7, 3), -1, np.float32), np.full((nf + 7, 3), -1, np.int64)
+    assert pkg.api.isosurface_into(a, vb, fb, m) == (nv, nf)
+    assert np.array_equal(fb[:nf], f0) and _bits_equal(vb[:nv], v0)
+    assert (fb[nf:] == -1).all() and (vb[nv:] == -1).all()
+    with pytest.raises(pkg.capi.B200IsoError):
+        pkg.api.isosurface_into(a, vb[:10], fb, m)
+    # the two-phase pair still works on the same handle afterwards
+    v2, f2 = pkg.isosurface(s, m)
+    assert np.array_equal(f2, f0) and _bits_equal(v2, v0)
+
+
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+def test_extract_host_on_a_sharded_slab(pkg, algo):
+    """A rank's slab (x_offset / nx_global / MT ghost row) through the one-shot call: slab-local indices."""
+    s = pkg.synth.gyroid((120, 30, 34))
+    m = _method(pkg, algo, 0.0, True)
+    xa, xb = pkg.sharding.slab_bounds(120, 3, 1, ghost=(algo == "MT"))
+    slab = np.asfortranarray(s[xa:xb])
+    v0, f0 = pkg.api.isosurface_slab(slab, m, xa, 120, 0)
+    p = pkg.api.make_params(m)
+    p.x_offset, p.nx_global, p.x_ghost = xa, 120, int(algo == "MT")
+    import os
+    os.environ["B200ISO_HOST_SLABS"] = "3"
+    try:
+        vb, fb = np.empty((len(v0), 3), np.float32), np.empty((len(f0), 3), np.int64)
+        nv, nf, _, fits = pkg.api.get_handle(0).extract_host(p, slab.ctypes.data, *slab.shape, slab.shape[0], vb.ctypes.data, len(vb), fb.ctypes.data, len(fb))
+    finally:
+        del os.environ["B200ISO_HOST_SLABS"]
+    assert fits and (nv, nf) == (len(v0), len(f0))
+    assert np.array_equal(fb, f0) and _bits_equal(vb, v0)
+
+
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+def test_host_paths_pinned_and_pageable_arrays(pkg, algo):
+    """Pinned caller arrays take the direct-DMA lanes, pageable ones the threaded pinned staging (several 8 MB chunks
+    per lane here); both entry points give the same bytes either way."""
+    import torch
+    n = (300, 260, 250)  # 78 MB field: multi-chunk, two slabs
+    s = pkg.synth.gyroid(n)
+    m = _method(pkg, algo, 0.0, True)
+    v0, f0 = pkg.isosurface(s, m)  # pageable, two-phase
+    pin = torch.empty(n[::-1], dtype=torch.float32).pin_memory()
+    a = pin.numpy().transpose(2, 1, 0)  # Fortran-ordered view of the pinned block
+    a[...] = s
+    assert a.flags.f_contiguous
+    vp = torch.empty((len(v0), 3), dtype=torch.float32).pin_memory().numpy()
+    fp = torch.empty((len(f0), 3), dtype=torch.int64).pin_memory().numpy()
+    h, p = pkg.api.get_handle(0), pkg.api.make_params(m)
+    h.count(p, a.ctypes.data, pkg.capi.HOST, *n, n[0])
+    h.generate(vp.ctypes.data, fp.ctypes.data, pkg.capi.HOST, 0)
+    assert np.array_equal(fp, f0) and _bits_equal(vp, v0)
+    vp[:], fp[:] = 0, 0
+    assert pkg.api.isosurface_into(a, vp, fp, m) == (len(v0), len(f0))  # pinned in, pinned out
+    assert np.array_equal(fp, f0) and _bits_equal(vp, v0)
+    v1, f1 = np.zeros_like(v0), np.zeros_like(f0)
+    assert pkg.api.isosurface_into(a, v1, f1, m) == (len(v0), len(f0))  # pinned in, pageable out
+    assert np.array_equal(f1, f0) and _bits_equal(v1, v0)
+    vp[:], fp[:] = 0, 0
+    assert pkg.api.isosurface_into(np.asfortranarray(s), vp, fp, m) == (len(v0), len(f0))  # pageable in, pinned out
+    assert np.array_equal(fp, f0) and _bits_equal(vp, v0)
