@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="mc_gyroid", choices=["mc_gyroid", "mt_gyroid", "mc_m2048"])
+    ap.add_argument("--workload", default="mc_gyroid", choices=["mc_gyroid", "mc_gyroid_strong", "mt_gyroid", "mc_m2048"])
     ap.add_argument("--n", type=int, default=0, help="override the base grid size (development)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -54,6 +54,11 @@ def workload_spec(name, n_override, world):
         return dict(algo="MC", shape=(n * world, n, n), kind="gyroid", n=n,
                     desc=f"MarchingCubes(iso=0f0), Float32 gyroid cos x sin y + cos y sin z + cos z sin x, "
                          f"{n * world}x{n}x{n} samples on [0,4pi*{world}]x[0,4pi]^2, x-slabs of {n} voxel planes per GPU")
+    if name == "mc_gyroid_strong":  # BASELINE configs[3] read literally: ONE 1024^3 volume sharded over the GPUs
+        n = n_override or 1024
+        return dict(algo="MC", shape=(n, n, n), kind="gyroid", n=n, scaling="strong",
+                    desc=f"MarchingCubes(iso=0f0), Float32 gyroid, one {n}x{n}x{n} volume on [0,4pi]^3 split into "
+                         f"{world} x-slabs of {n // world} voxel planes (strong scaling)")
     if name == "mt_gyroid":
         n = n_override or 512
         return dict(algo="MT", shape=(n * world, n, n), kind="gyroid", n=n,
@@ -231,7 +236,7 @@ def run_reference(args, rank):
     sample = f"voxel x-planes [0,{planes}) of the {nx}x{ny}x{nz} field ({planes * per_plane} voxels per step), full-field strides"
     line = {"impl": "reference", "metric": "isosurface throughput, " + spec["desc"], "value": value, "unit": "Gvoxels/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 field, f64 positions, f32 vertices, int64 faces",
+            "scaling": spec.get("scaling", "weak"), "vs_baseline": None, "dtype": "f32 field, f64 positions, f32 vertices, int64 faces",
             "data": "synthetic", "config": {"workload": args.workload, "shape": [nx, ny, nz], "sample": sample},
             "cpu_baseline": {"value": value, "unit": "Gvoxels/s", "cores": threads, "kind": "port", "sample": sample,
                              "note": "C++ restatement of Meshing.jl's loops (oracle/iso_oracle.cpp); Julia is not installed"},
@@ -414,7 +419,7 @@ def main():
             "metric": "isosurface throughput (Gvoxels/s; Mtriangles/s alongside), " + spec["desc"],
             "value": value, "unit": "Gvoxels/s", "mtriangles_per_s": mtri,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": spec.get("scaling", "weak"), "vs_baseline": None,
             "dtype": "f32 field, f64 positions, f32 vertices, int64 faces" if not f64 else "f32 field, f64 positions and vertices, int64 faces",
             "data": "synthetic",
             "config": {"workload": args.workload, "shape": [nxg, ny, nz], "per_gpu_shape": [nxl, ny, nz], "algo": spec["algo"],
