@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--workload", default="mc_gyroid", choices=["mc_gyroid", "mc_gyroid_strong", "mt_gyroid", "mc_m2048"])
     ap.add_argument("--n", type=int, default=0, help="override the base grid size (development)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="sharded runs: how the slab totals travel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
     return ap.parse_args()
@@ -295,15 +296,39 @@ def main():
     vbase = torch.zeros(1, dtype=torch.int64, device=device)
     sharded = world > 1 and not spec.get("replicas")
 
+    # the one exchange of the sharded path: every slab's (nverts, nfaces), 16 bytes per rank; the exclusive prefix is
+    # the slab's global vertex base, added to its face indices inside generate.  Preferred form: peer-memory stores
+    # over NVLink on the handle's own stream (b200iso_exchange_async); NCCL all-gather if the ranks cannot map each
+    # other's memory (or --exchange nccl).
+    px, exchange = None, "none"
+    if sharded:
+        exchange = "nccl all-gather"
+        if args.exchange == "peer":
+            try:
+                px = pkg.sharding.PeerExchange(h, device=device)
+                exchange = "NVLink peer-memory stores (b200iso_exchange_async)"
+            except Exception as e:  # pragma: no cover
+                ok = torch.tensor([0], device=device)
+                exchange = f"nccl all-gather (peer mapping failed: {type(e).__name__})"
+            else:
+                ok = torch.tensor([1], device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # all ranks take the same path
+            if not bool(ok.item()) and px is not None:
+                px.close()
+                px, exchange = None, "nccl all-gather (peer mapping failed on another rank)"
+
     def step():
-        # classify -> count + decoupled look-back scan -> [all-gather of the slab totals] -> generate; all asynchronous
+        # classify -> count + decoupled look-back scan -> [exchange of the slab totals] -> generate; all asynchronous
         h.count_async(params, field.data_ptr(), nxl, ny, nz, ldx, totals.data_ptr())
-        if sharded:
-            # the one exchange of the sharded path: every slab's (nverts, nfaces), 16 bytes per rank; its
-            # exclusive prefix is this slab's global vertex base, added to the slab's face indices in generate
+        if px is not None:
+            base_ptr = px.exchange_async()
+        elif sharded:
             dist.all_gather_into_tensor(gathered.view(-1), totals)
             torch.sum(gathered[:rank, 0], dim=0, keepdim=True, out=vbase)
-        h.generate_async(verts.data_ptr(), verts.shape[0], faces.data_ptr(), faces.shape[0], vbase.data_ptr() if sharded else 0, 0)
+            base_ptr = vbase.data_ptr()
+        else:
+            base_ptr = 0
+        h.generate_async(verts.data_ptr(), verts.shape[0], faces.data_ptr(), faces.shape[0], base_ptr, 0)
 
     def barrier():
         if world > 1:
@@ -401,6 +426,11 @@ def main():
                "pageable": {"value": tot_vox / dt_pag / 1e9, "ms_per_step": dt_pag * 1e3,
                             "api": "b200iso_count(HOST) + b200iso_generate(HOST) on pageable arrays (threaded pinned staging)"}}
         # sanity: host result of the last step equals the device-resident result
+        if px is not None:
+            vbase.copy_(px.bases[:1])
+            # the peer exchange must agree with an NCCL all-gather of the same totals
+            dist.all_gather_into_tensor(gathered.view(-1), totals)
+            assert torch.equal(px.all, gathered) and int(vbase.item()) == int(gathered[:rank, 0].sum().item())
         assert torch.equal(hfaces[:nf], faces[:nf].cpu() - int(vbase.item()) if sharded else faces[:nf].cpu())
 
     if rank == 0:
@@ -423,7 +453,8 @@ def main():
             "dtype": "f32 field, f64 positions, f32 vertices, int64 faces" if not f64 else "f32 field, f64 positions and vertices, int64 faces",
             "data": "synthetic",
             "config": {"workload": args.workload, "shape": [nxg, ny, nz], "per_gpu_shape": [nxl, ny, nz], "algo": spec["algo"],
-                       "sharding": ("x-slabs + one 16-byte all-gather of counts" if sharded else ("replicas" if world > 1 else "single GPU")),
+                       "sharding": ("x-slabs + one 16-byte exchange of counts" if sharded else ("replicas" if world > 1 else "single GPU")),
+                       "exchange": exchange,
                        "l2": "inputs larger than L2 (field %.2f GB per GPU, read once per step)" % (4.0 * nxl * ny * nz / 1e9),
                        "mesh": {"nverts": tot_nv, "nfaces": tot_nf}},
             "roofline": {"bound": "hbm", "kernel": kname[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -137,6 +137,24 @@ int b200iso_set_extract_mode(b200iso_handle* h, int mode);
 int b200iso_add_vertex_base_async(b200iso_handle* h, int64_t* faces_dev, int64_t fcap, const int64_t* totals_dev,
                                   const int64_t* vertex_base_dev);
 
+/* ---- sharded path: exchange of the slabs' totals over NVLink peer memory ------------------------------------
+ * The sharded path's only exchange is 16 bytes per rank (nverts, nfaces of its x-slab).  Instead of
+ * an NCCL all-gather it can run as plain peer-memory stores inside the handle's stream:
+ * b200iso_set_peer_exchange: slots[r] = device pointer, valid on THIS device, of rank r's exchange buffer
+ *                       (B200ISO_PEER_BYTES bytes, zeroed once, mapped into every rank: CUDA IPC or torch symmetric
+ *                       memory; slots[rank] is this rank's own buffer).  world <= 1 or slots == NULL switches it off.
+ * b200iso_exchange_async : after a count: publishes this rank's totals into every rank's buffer (release.sys P2P
+ *                       stores over NVLink), waits for everyone's in the local buffer and writes
+ *                       bases_dev[0..3] = {vertex base, face base of this rank, total nverts, total nfaces};
+ *                       all_dev (may be NULL) receives every rank's (nverts, nfaces).  Pass bases_dev as
+ *                       vertex_base_dev to b200iso_generate_async.  Every rank must call it once per count (the
+ *                       calls are matched by an epoch counter); a rank that never arrives makes the others fail
+ *                       after about a second (B200ISO_ESTATE from b200iso_totals) instead of hanging. */
+#define B200ISO_PEER_MAX 16
+#define B200ISO_PEER_BYTES (2 * B200ISO_PEER_MAX * 4 * 8)
+int b200iso_set_peer_exchange(b200iso_handle* h, int rank, int world, void* const* slots);
+int b200iso_exchange_async(b200iso_handle* h, int64_t* bases_dev, int64_t* all_dev);
+
 /* ---- one-shot host form (host arrays in, host arrays out, capacity known up front) ----------------------
  * b200iso_extract_host: the whole isosurface() of a HOST field into caller-owned HOST arrays of capacity vcap
  *                       vertices / fcap faces, as an x-slab software pipeline over three streams: strided H2D of

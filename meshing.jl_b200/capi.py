@@ -15,6 +15,8 @@ HEADER = os.path.join(ROOT, "include", "b200iso.h")
 MC, MT = 0, 1
 HOST, DEVICE = 0, 1
 ECAPACITY = -5  # B200ISO_ECAPACITY
+PEER_MAX = 16
+PEER_BYTES = 2 * PEER_MAX * 4 * 8  # B200ISO_PEER_BYTES
 RANGE_INT, RANGE_F32, RANGE_F64 = 0, 1, 2
 
 
@@ -73,6 +75,8 @@ def load():
     L.b200iso_totals.argtypes = [vp, pi64, pi64, pci]
     L.b200iso_extract_async.argtypes = [vp, pp, vp, i64, i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]
     L.b200iso_extract_host.argtypes = [vp, pp, vp, i64, i64, i64, i64, vp, i64, vp, i64, pi64, pi64, pci]
+    L.b200iso_set_peer_exchange.argtypes = [vp, ci, ci, ctypes.POINTER(vp)]
+    L.b200iso_exchange_async.argtypes = [vp, vp, vp]
     L.b200iso_add_vertex_base_async.argtypes = [vp, vp, i64, vp, vp]
     L.b200iso_set_extract_mode.argtypes = [vp, ci]
     L.b200iso_case_indices.argtypes = [vp, vp, ci]
@@ -151,6 +155,17 @@ class Handle:
         if rc != ECAPACITY:
             _check(rc)
         return nv.value, nf.value, bool(f64.value), rc == 0
+
+    def set_peer_exchange(self, rank, world, slot_ptrs):
+        """slot_ptrs[r] = device pointer (valid on this device) of rank r's PEER_BYTES exchange buffer; None switches it off."""
+        if not slot_ptrs or world <= 1:
+            _check(self.L.b200iso_set_peer_exchange(self.h, 0, 0, None))
+            return
+        arr = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p)) for p in slot_ptrs])
+        _check(self.L.b200iso_set_peer_exchange(self.h, rank, world, arr))
+
+    def exchange_async(self, bases_dev_ptr, all_dev_ptr=0):
+        _check(self.L.b200iso_exchange_async(self.h, ctypes.c_void_p(bases_dev_ptr), ctypes.c_void_p(all_dev_ptr or 0)))
 
     def set_extract_mode(self, mode):
         """0 = count then generate (default), 1 = fused single-pass kernel"""

@@ -93,7 +93,11 @@ struct b200iso_handle {
   hostpipe::Pool pool;             // copy lanes (streams, pinned chunks, events) of the HOST paths
   std::vector<cudaEvent_t> slab_ev;  // b200iso_extract_host: slab k generated; [n-2] fork, [n-1] join
   unsigned int* ticket = nullptr;
-  long long* totals_dev = nullptr;   // device int64[2]
+  long long* totals_dev = nullptr;   // device int64[4]: nverts, nfaces, peer-exchange error flag, spare
+  // sharded path: peer exchange of the slab totals (b200iso_set_peer_exchange)
+  iso::PeerSlots peers{};
+  int peer_rank = 0, peer_world = 0;
+  long long peer_epoch = 0;
   long long* totals_host = nullptr;  // pinned int64[2]
   // last counted problem
   bool counted = false, totals_known = false;
@@ -283,8 +287,12 @@ int enqueue_generate(b200iso_handle* h, void* verts_dev, int64_t vcap, int64_t* 
 int fetch_totals(b200iso_handle* h) {
   if (!h->counted) return fail(B200ISO_ESTATE, "no counted field");
   if (!h->totals_known) {
-    CU(cudaMemcpyAsync(h->totals_host, h->totals_dev, 2 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->totals_host, h->totals_dev, 3 * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    if (h->totals_host[2] != 0) {
+      cudaMemsetAsync(h->totals_dev + 2, 0, sizeof(long long), h->stream);
+      return fail(B200ISO_ESTATE, "peer exchange timed out: a rank did not publish its totals");
+    }
     h->nverts = h->totals_host[0], h->nfaces = h->totals_host[1];
     h->totals_known = true;
   }
@@ -314,8 +322,9 @@ int b200iso_create(b200iso_handle** out, int device) {
   CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
   CU(cudaMalloc((void**)&h->ticket, sizeof(unsigned int)));
-  CU(cudaMalloc((void**)&h->totals_dev, 2 * sizeof(long long)));
-  CU(cudaMallocHost((void**)&h->totals_host, 2 * sizeof(long long)));
+  CU(cudaMalloc((void**)&h->totals_dev, 4 * sizeof(long long)));
+  CU(cudaMemset(h->totals_dev, 0, 4 * sizeof(long long)));
+  CU(cudaMallocHost((void**)&h->totals_host, 4 * sizeof(long long)));
   *out = h;
   return 0;
 }
@@ -395,6 +404,38 @@ int b200iso_add_vertex_base_async(b200iso_handle* h, int64_t* faces_dev, int64_t
                                                        (const long long*)vertex_base_dev);
   CU(cudaGetLastError());
   h->launches++;
+  return 0;
+}
+
+int b200iso_set_peer_exchange(b200iso_handle* h, int rank, int world, void* const* slots) {
+  if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  if (world <= 1 || !slots) {
+    h->peer_world = 0;
+    return 0;
+  }
+  if (world > iso::PEER_MAX || rank < 0 || rank >= world) return fail(B200ISO_EINVAL, "bad rank/world %d/%d (at most %d ranks)", rank, world, iso::PEER_MAX);
+  for (int r = 0; r < world; ++r) {
+    if (!slots[r]) return fail(B200ISO_EINVAL, "slots[%d] is NULL", r);
+    h->peers.slot[r] = (long long*)slots[r];
+  }
+  h->peer_rank = rank, h->peer_world = world, h->peer_epoch = 0;
+  return 0;
+}
+
+int b200iso_exchange_async(b200iso_handle* h, int64_t* bases_dev, int64_t* all_dev) {
+  if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  if (!h->counted) return fail(B200ISO_ESTATE, "exchange called before count");
+  if (h->peer_world <= 1) return fail(B200ISO_ESTATE, "no peer exchange configured (b200iso_set_peer_exchange)");
+  if (!bases_dev) return fail(B200ISO_EINVAL, "bases_dev is NULL");
+  CU(cudaSetDevice(h->device));
+  const long long epoch = ++h->peer_epoch;
+  iso::peer_publish_kernel<<<1, 32, 0, h->stream>>>(h->peers, h->peer_world, h->peer_rank, epoch, h->totals_dev);
+  CU(cudaGetLastError());
+  iso::peer_gather_kernel<<<1, 32, 0, h->stream>>>(h->peers.slot[h->peer_rank], h->peer_world, h->peer_rank, epoch, (long long*)bases_dev,
+                                                   (long long*)all_dev, h->totals_dev + 2);
+  CU(cudaGetLastError());
+  h->launches += 2;
+  h->totals_known = false;  // the next b200iso_totals re-reads the totals together with the exchange's error flag
   return 0;
 }
 

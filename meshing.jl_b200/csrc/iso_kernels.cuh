@@ -377,6 +377,63 @@ __device__ __forceinline__ void lookback(unsigned long long* status, long long b
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Sharded path: exchange of the slabs' totals over NVLink peer memory (instead of a 16-byte NCCL all-gather).
+// Every rank owns an exchange buffer int64[2][PEER_MAX][4] that all ranks have mapped (CUDA IPC / symmetric memory);
+// slot [epoch & 1][r] of it is written by rank r only: {nverts, nfaces, 0, epoch}, the epoch word last with
+// release.sys.  Two parities suffice: rank r can publish epoch e + 2 only after its generate of epoch e + 1, which
+// waited for everyone's count of epoch e + 1, which (stream order) follows everyone's gather of epoch e.
+constexpr int PEER_MAX = 16;
+struct PeerSlots {
+  long long* slot[PEER_MAX];
+};
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
+  asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+  long long v;
+  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// one warp: lane r stores this rank's totals into rank r's buffer (a P2P store over NVLink for r != rank)
+__global__ void peer_publish_kernel(PeerSlots ps, int world, int rank, long long epoch, const long long* __restrict__ totals) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  long long* s = ps.slot[r] + ((epoch & 1) * PEER_MAX + rank) * 4;
+  s[0] = totals[0], s[1] = totals[1], s[2] = 0;
+  st_release_sys(s + 3, epoch);
+}
+// one warp: lane r waits for rank r's totals of this epoch in the LOCAL buffer; bases[0..1] = exclusive prefix of
+// (nverts, nfaces) over the ranks below this one, bases[2..3] = grand totals; optionally all pairs to `all`.
+// A peer that never arrives trips the timeout (about a second) instead of hanging the GPU: *err = 1.
+__global__ void peer_gather_kernel(const long long* mine, int world, int rank, long long epoch, long long* __restrict__ bases,
+                                   long long* __restrict__ all, long long* err) {
+  const int r = threadIdx.x;
+  long long nv = 0, nf = 0;
+  bool ok = true;
+  if (r < world) {
+    const long long* s = mine + ((epoch & 1) * PEER_MAX + r) * 4;
+    long long spins = 0;
+    while (ld_acquire_sys(s + 3) != epoch) {
+      __nanosleep(200);
+      if (++spins > 4000000) {
+        ok = false;
+        break;
+      }
+    }
+    nv = s[0], nf = s[1];
+    if (all) all[2 * r] = nv, all[2 * r + 1] = nf;
+  }
+  if (!__all_sync(0xffffffffu, ok) && r == 0) *err = 1;
+  long long bv = r < rank ? nv : 0, bf = r < rank ? nf : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    bv += __shfl_xor_sync(0xffffffffu, bv, o), bf += __shfl_xor_sync(0xffffffffu, bf, o);
+    nv += __shfl_xor_sync(0xffffffffu, nv, o), nf += __shfl_xor_sync(0xffffffffu, nf, o);
+  }
+  if (r == 0) bases[0] = bv, bases[1] = bf, bases[2] = nv, bases[3] = nf;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // coordinates: LinRange(first, last, n)[i] = P((1-t)*a + t*b), t = i/(n-1) in Float64 (Julia Base lerpi,
 // SURVEY.md A2).  Stored as doubles (a Float32 value is exact in a double).
 __global__ void coords_kernel(double* out, int nx, int ny, int nz, double x0, double x1, double y0, double y1, double z0,

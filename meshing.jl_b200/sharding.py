@@ -49,3 +49,40 @@ def stitch(parts):
     v = np.concatenate([p[0] for p in parts]) if parts else np.empty((0, 3), np.float32)
     f = np.concatenate([p[1] for p in parts]) if parts else np.empty((0, 3), np.int64)
     return v, f
+
+
+class PeerExchange:
+    """The same exchange without NCCL in the data path: every rank's 16 bytes go to every rank as peer-memory stores
+    over NVLink, enqueued on the handle's own stream (b200iso_set_peer_exchange / b200iso_exchange_async).
+    torch's symmetric memory does the plumbing: it allocates one PEER_BYTES buffer per rank and maps all of them
+    into every process.  Raises if the ranks cannot map each other's memory (callers then keep the all-gather)."""
+
+    def __init__(self, handle, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        from . import capi
+
+        group = group or dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > capi.PEER_MAX:
+            raise ValueError(f"at most {capi.PEER_MAX} ranks")
+        device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm.empty(capi.PEER_BYTES // 8, dtype=torch.int64, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, group)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)  # every buffer is zero before anyone publishes
+        self.handle = handle
+        handle.set_peer_exchange(self.rank, self.world, [int(p) for p in self.hdl.buffer_ptrs])
+        self.bases = torch.zeros(4, dtype=torch.int64, device=device)       # vertex base, face base, total nverts, total nfaces
+        self.all = torch.zeros((self.world, 2), dtype=torch.int64, device=device)
+
+    def exchange_async(self):
+        """After handle.count_async: publish + gather on the handle's stream; returns the device pointer to pass as
+        vertex_base_dev to generate_async."""
+        self.handle.exchange_async(self.bases.data_ptr(), self.all.data_ptr())
+        return self.bases.data_ptr()
+
+    def close(self):
+        self.handle.set_peer_exchange(0, 0, None)

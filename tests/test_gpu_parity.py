@@ -545,3 +545,67 @@ def test_host_paths_pinned_and_pageable_arrays(pkg, algo):
     vp[:], fp[:] = 0, 0
     assert pkg.api.isosurface_into(np.asfortranarray(s), vp, fp, m) == (len(v0), len(f0))  # pageable in, pinned out
     assert np.array_equal(fp, f0) and _bits_equal(vp, v0)
+
+
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+def test_peer_exchange_two_ranks_on_one_gpu(pkg, oracle, algo):
+    """b200iso_exchange_async (the NVLink peer-memory form of the 16-byte all-gather): two handles play two ranks on
+    one device, each publishing into both exchange buffers; several epochs exercise the parity double-buffering."""
+    import torch
+    s = pkg.synth.gyroid((61, 30, 33))
+    m = _method(pkg, algo, 0.0, True)
+    world = 2
+    bufs = [torch.zeros(pkg.capi.PEER_BYTES // 8, dtype=torch.int64, device="cuda") for _ in range(world)]
+    hs = [pkg.capi.Handle(0) for _ in range(world)]
+    for r, h in enumerate(hs):
+        h.set_peer_exchange(r, world, [b.data_ptr() for b in bufs])
+    vo, fo = oracle.isosurface(s, ALGOS[algo], iso=0.0, iso_is_f32=True, eps_is_f32=True)
+    slabs, prm = [], []
+    for r in range(world):
+        xa, xb = pkg.sharding.slab_bounds(61, world, r, ghost=(algo == "MT"))
+        slabs.append(torch.from_numpy(np.asfortranarray(s[xa:xb]).transpose(2, 1, 0).copy()).cuda().permute(2, 1, 0))
+        p = pkg.api.make_params(m)
+        p.x_offset, p.nx_global, p.x_ghost = xa, 61, int(algo == "MT" and r > 0)
+        prm.append(p)
+    torch.cuda.synchronize()  # the handles run on their own streams
+    bases = [torch.zeros(4, dtype=torch.int64, device="cuda") for _ in range(world)]
+    allc = [torch.zeros((world, 2), dtype=torch.int64, device="cuda") for _ in range(world)]
+    for epoch in range(3):
+        for r, h in enumerate(hs):  # every "rank" counts and publishes before anyone has to wait
+            t = slabs[r]
+            h.count_async(prm[r], t.data_ptr(), t.shape[0], t.shape[1], t.shape[2], t.stride(1))
+        for r, h in enumerate(hs):
+            h.exchange_async(bases[r].data_ptr(), allc[r].data_ptr())
+        parts = []
+        for r, h in enumerate(hs):
+            nv, nf, _ = h.totals()
+            v = torch.empty((nv, 3), dtype=torch.float32, device="cuda")
+            f = torch.empty((nf, 3), dtype=torch.int64, device="cuda")
+            h.generate_async(v.data_ptr(), nv, f.data_ptr(), nf, bases[r].data_ptr(), 0)
+            h.totals()  # (synchronises the handle's stream)
+            torch.cuda.synchronize()
+            parts.append((v.cpu().numpy(), f.cpu().numpy()))
+        v, f = pkg.sharding.stitch(parts)
+        assert np.array_equal(f, fo) and _bits_equal(v, vo)
+        assert torch.equal(allc[0], allc[1]) and int(bases[1][0]) == len(parts[0][0]) and int(bases[0][2]) == len(vo)
+
+
+def test_peer_exchange_timeout_reports_instead_of_hanging(pkg):
+    """A rank that never publishes: the waiting rank gives up after about a second and the next totals() fails."""
+    import torch
+    s = pkg.synth.sphere((20, 20, 20))
+    bufs = [torch.zeros(pkg.capi.PEER_BYTES // 8, dtype=torch.int64, device="cuda") for _ in range(2)]
+    h = pkg.capi.Handle(0)
+    h.set_peer_exchange(0, 2, [b.data_ptr() for b in bufs])
+    t = torch.from_numpy(np.ascontiguousarray(s.transpose(2, 1, 0))).cuda().permute(2, 1, 0)
+    p = pkg.api.make_params(pkg.MarchingCubes(iso=pkg.Float32(0)))
+    torch.cuda.synchronize()
+    h.count_async(p, t.data_ptr(), 20, 20, 20, t.stride(1))
+    bases = torch.zeros(4, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    h.exchange_async(bases.data_ptr())
+    with pytest.raises(pkg.capi.B200IsoError):
+        h.totals()
+    h.set_peer_exchange(0, 0, None)
+    h.count_async(p, t.data_ptr(), 20, 20, 20, t.stride(1))
+    assert h.totals()[0] > 0  # the handle is usable again
