@@ -269,6 +269,7 @@ struct Downloader {
     for (auto& th : threads)
       if (th.joinable()) th.join();
     threads.clear();
+    if (!pool || pool->out.empty()) return cudaSuccess;  // never started
     if (pinned) return cudaStreamSynchronize(pool->out[0].stream);
     return (cudaError_t)err.load();
   }

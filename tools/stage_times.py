@@ -6,6 +6,7 @@ import numpy as np, torch
 from __graft_entry__ import load_package
 pkg = load_package()
 algo = sys.argv[1] if len(sys.argv) > 1 else "MC"
+f64 = "f64" in sys.argv  # Float64 field (and therefore Float64 vertices)
 fused = any(a.startswith("mode") for a in sys.argv)
 mode = int([a for a in sys.argv if a.startswith("mode")][0][4:]) if fused else 0
 sizes = [int(a) for a in sys.argv[2:] if a.isdigit()] or [256, 512, 1024]
@@ -14,9 +15,12 @@ h.enable_timing(True)
 h.set_extract_mode(mode)
 for n in sizes:
     t = pkg.synth.gyroid_torch(n, "cuda")
+    if f64:
+        t = (t.permute(2, 1, 0).contiguous().double() * 1.0000000001).permute(2, 1, 0)  # same layout, Float64 samples
     torch.cuda.synchronize()
     m = pkg.MarchingCubes(iso=pkg.Float32(0)) if algo == "MC" else pkg.MarchingTetrahedra(iso=pkg.Float32(0), eps=pkg.Float32(1e-3))
     p = pkg.api.make_params(m)
+    p.field_is_f64 = int(f64)
     for it in range(8):
         if it == 3:
             h.enable_timing(True)  # resets the ring: average over the last 5 iterations only
@@ -24,7 +28,7 @@ for n in sizes:
             h.extract_async(p, t.data_ptr(), n, n, n, t.stride(1), verts.data_ptr(), nv, faces.data_ptr(), nf)
         else:
             nv, nf, f64 = h.count(p, t.data_ptr(), pkg.capi.DEVICE, n, n, n, t.stride(1))
-            verts = torch.empty((nv, 3), dtype=torch.float32, device="cuda")
+            verts = torch.empty((nv, 3), dtype=torch.float64 if f64 else torch.float32, device="cuda")
             faces = torch.empty((nf, 3), dtype=torch.int64, device="cuda")
             h.generate(verts.data_ptr(), faces.data_ptr(), pkg.capi.DEVICE, 0)
         tm = h.timings()
@@ -39,7 +43,8 @@ for n in sizes:
         e1.record(); torch.cuda.synchronize()
         tot = e0.elapsed_time(e1) / 10
         h.use_own_stream()
-    B = 4 * n ** 3 + 12 * nv + 24 * nf
+    esz = 8 if f64 else 4
+    B = esz * n ** 3 + 3 * esz * nv + 24 * nf
     print(f"{algo}{" mode%d" % mode if fused else ""} n={n} nv={nv} nf={nf} classify={tm['classify_ms']:.3f} count={tm['count_scan_ms']:.3f} gen={tm['generate_ms']:.3f} "
-          f"total={tot:.3f} ms  {(n-1)**3/tot/1e6:.1f} Gvox/s  {B/tot/1e6:.0f} GB/s  classify {4*n**3/tm['classify_ms']/1e6:.0f} GB/s", flush=True)
+          f"total={tot:.3f} ms  {(n-1)**3/tot/1e6:.1f} Gvox/s  {B/tot/1e6:.0f} GB/s  classify {esz*n**3/tm['classify_ms']/1e6:.0f} GB/s", flush=True)
     del t, verts, faces
