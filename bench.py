@@ -439,7 +439,7 @@ def main():
         alg = {"classify": 4.0 * nxl * ny * nz, "count_scan": 0.0, "generate": float(vbytes * nv + 24 * nf)}
         w16 = ((nz + 31) // 32 + 15) // 16
         tma = ((nxl + 127) // 128) * ny * w16 >= 4096 and os.environ.get("B200ISO_TMA", "1") != "0"  # the library's rule
-        kname = {"classify": "signpack_tma_kernel" if tma else "signpack_kernel", "count_scan": "mc_count_warp_kernel" if spec["algo"] == "MC" else "count_kernel", "generate": "mc_generate_kernel" if spec["algo"] == "MC" else "mt_generate_kernel"}
+        kname = {"classify": "signpack_tma_kernel" if tma else "signpack_kernel", "count_scan": "mc_count_chunks_kernel" if spec["algo"] == "MC" else "count_kernel", "generate": "mc_generate_kernel" if spec["algo"] == "MC" else "mt_generate_kernel"}
         stage_ms = {"classify": stage["classify_ms"], "count_scan": stage["count_scan_ms"], "generate": stage["generate_ms"]}
         dom = max(stage_ms, key=lambda k: stage_ms[k])
         achieved = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0

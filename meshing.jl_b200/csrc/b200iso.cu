@@ -116,6 +116,7 @@ struct b200iso_handle {
   unsigned char* ev_set = nullptr;    // which events of a slot were recorded
   long long step = 0;                 // steps (count calls) since timing was enabled
   int64_t launches = 0;
+  int split_count = 1;  // MC: count chunks, then scan them (1, default) or count with the look-back chain inside (0; env B200ISO_SPLIT_COUNT)
   int tma_mode = -1;  // classify staging: -1 = TMA boxes on big fields (default), 1 = always TMA, 0 = per-lane 128-bit loads (env B200ISO_TMA)
   int mode = 0;  // b200iso_extract_async strategy for MC: 0 = count then generate, 1 = fused single pass
   int rec(int which) {
@@ -224,6 +225,13 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
   CU(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int), st));
   h->totals_out = totals_out;
   if (fused) {
+  } else if (p->algo == B200ISO_MC && h->split_count) {
+    // (a) raw per-chunk counts, (b) light single-pass look-back scan over them (count_kernel.cuh)
+    iso::mc_count_chunks_kernel<<<(unsigned)h->chain_blocks, iso::WC_THREADS, 0, st>>>(h->bits.p, g, h->nblocks, h->woff.p);
+    CU(cudaGetLastError());
+    h->launches++;
+    const long long per = (long long)iso::SC_THREADS * iso::SC_PER, nsb = (h->nblocks + per - 1) / per;
+    iso::mc_scan_chunks_kernel<<<(unsigned)nsb, iso::SC_THREADS, 0, st>>>(h->woff.p, h->nblocks, h->status.p, h->ticket, nsb, h->totals_dev, totals_out);
   } else if (p->algo == B200ISO_MC)
     iso::mc_count_warp_kernel<<<(unsigned)h->chain_blocks, iso::WC_THREADS, 0, st>>>(h->bits.p, g, h->nblocks, h->status.p, h->ticket,
                                                                                    h->chain_blocks, h->totals_dev, totals_out, h->woff.p);
@@ -317,6 +325,7 @@ int b200iso_create(b200iso_handle** out, int device) {
   h->device = device;
   h->pool.device = device;
   if (const char* e = getenv("B200ISO_TMA")) h->tma_mode = atoi(e) != 0 ? 1 : 0;
+  if (const char* e = getenv("B200ISO_SPLIT_COUNT")) h->split_count = atoi(e) != 0 ? 1 : 0;
   // per device: the TMA classify kernel needs more than the default 48 KB of dynamic shared memory
   CU(cudaFuncSetAttribute(iso::signpack_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iso::TM_SMEM));
   CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));

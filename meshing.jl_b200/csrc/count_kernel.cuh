@@ -173,4 +173,105 @@ mc_count_warp_kernel(const uint32_t* __restrict__ bits, Grid g, long long nchunk
   }
 }
 
+
+// ---- split form: counting and scanning in two kernels -----------------------------------------------------
+// In mc_count_warp_kernel the look-back chain runs over the counting blocks themselves: a block that sits on a dense
+// piece of surface counts for much longer than its neighbours, and every block behind it in the chain finishes its
+// own work and then waits for that one aggregate.  On fields with clustered surfaces (multi-sphere/torus: 0.35 ms)
+// that costs more than the counting.  Split: (a) every warp counts its chunk and stores the raw pair -- no chain, no
+// ticket, no barrier; (b) a single-pass decoupled look-back scan over the stored pairs, whose blocks are uniform
+// and tiny (1024 pairs each), turns them into exclusive prefixes in place.
+__global__ void __launch_bounds__(WC_THREADS)
+mc_count_chunks_kernel(const uint32_t* __restrict__ bits, Grid g, long long nchunks, unsigned long long* __restrict__ woff) {
+  __shared__ uint8_t nf_s[256];
+  nf_s[threadIdx.x] = (uint8_t)((ISO_MC_VERTS[threadIdx.x] >> 52) & 7);
+  __syncthreads();
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long chunk = (long long)blockIdx.x * (WC_THREADS / 32) + w;
+  if (chunk >= nchunks) return;
+  uint32_t nv = 0, nf = 0;
+  const int x = (int)(chunk / g.blocks_per_row);
+  const int q_lo = (int)(chunk - (long long)x * g.blocks_per_row) * CB_THREADS;
+  for (int q0 = q_lo; q0 < q_lo + CB_THREADS && q0 < g.quads_per_row; q0 += 32) {
+    const int qr = q0 + lane;
+    const int y = qr / g.Wq, zq = qr - y * g.Wq;
+    Quad q;
+    if (qr < g.quads_per_row && load_quad(bits, g, x, y, zq, q)) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t mm = active_mask(q, i);
+        if (mm) {
+          nv += mc_nverts_masked(q, i, q.vm[i]);
+          while (mm) {
+            const int k = __ffs(mm) - 1;
+            mm &= mm - 1;
+            nf += nf_s[case_of<0>(q, i, k)];
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nv += __shfl_xor_sync(0xffffffffu, nv, o);
+    nf += __shfl_xor_sync(0xffffffffu, nf, o);
+  }
+  if (lane == 0) woff[2 * chunk] = nv, woff[2 * chunk + 1] = nf;
+}
+
+constexpr int SC_THREADS = 256, SC_PER = 4;  // scan block: 1024 (vertex, face) pairs
+// In-place exclusive scan of the nchunks pairs in woff: block-local scan (shuffles), decoupled look-back across the
+// scan blocks (ticketed), totals from the last block.
+__global__ void __launch_bounds__(SC_THREADS)
+mc_scan_chunks_kernel(unsigned long long* __restrict__ woff, long long nchunks, unsigned long long* status, unsigned int* ticket,
+                      long long nsb, long long* totals_a, long long* totals_b) {
+  __shared__ unsigned long long wsum_v[SC_THREADS / 32], wsum_f[SC_THREADS / 32];
+  __shared__ unsigned long long base_s[2];
+  __shared__ unsigned sb;
+  if (threadIdx.x == 0) sb = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const long long b = sb;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long i0 = (b * SC_THREADS + threadIdx.x) * SC_PER;
+  unsigned long long v[SC_PER], f[SC_PER], tv = 0, tf = 0;
+#pragma unroll
+  for (int k = 0; k < SC_PER; ++k) {
+    const bool in = i0 + k < nchunks;
+    v[k] = in ? woff[2 * (i0 + k)] : 0ull, f[k] = in ? woff[2 * (i0 + k) + 1] : 0ull;
+    tv += v[k], tf += f[k];
+  }
+  unsigned long long iv = tv, jf = tf;  // inclusive over the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long a = __shfl_up_sync(0xffffffffu, iv, o), c = __shfl_up_sync(0xffffffffu, jf, o);
+    if (lane >= o) iv += a, jf += c;
+  }
+  if (lane == 31) wsum_v[w] = iv, wsum_f[w] = jf;
+  __syncthreads();
+  unsigned long long wbv = 0, wbf = 0, av = 0, af = 0;
+#pragma unroll
+  for (int k = 0; k < SC_THREADS / 32; ++k) {
+    if (k < w) wbv += wsum_v[k], wbf += wsum_f[k];
+    av += wsum_v[k], af += wsum_f[k];
+  }
+  if (w == 0) {
+    unsigned long long ev, ef;
+    lookback(status, b, av, af, ev, ef);
+    if (lane == 0) {
+      base_s[0] = ev, base_s[1] = ef;
+      if (b == nsb - 1) {
+        totals_a[0] = (long long)(ev + av), totals_a[1] = (long long)(ef + af);
+        if (totals_b) totals_b[0] = (long long)(ev + av), totals_b[1] = (long long)(ef + af);
+      }
+    }
+  }
+  __syncthreads();
+  unsigned long long pv = base_s[0] + wbv + (iv - tv), pf = base_s[1] + wbf + (jf - tf);
+#pragma unroll
+  for (int k = 0; k < SC_PER; ++k) {
+    if (i0 + k < nchunks) woff[2 * (i0 + k)] = pv, woff[2 * (i0 + k) + 1] = pf;
+    pv += v[k], pf += f[k];
+  }
+}
+
 }  // namespace iso

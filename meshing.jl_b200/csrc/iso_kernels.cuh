@@ -664,6 +664,14 @@ mc_generate_kernel(GenArgs a, Grid g) {
 
   const int tid = threadIdx.x;
   const unsigned b = block_id<FUSED>(a.ticket, &s_b);
+  if (!FUSED) {
+    // the count kernel left every block's exclusive prefix: a block whose successor starts at the same vertex has
+    // no active voxel (each one emits >= 3 vertices) -- leave before touching the bit-field.  On sparse fields
+    // (a few shapes in a big volume) that is most blocks.
+    const unsigned long long v0 = a.woff[2 * (unsigned long long)b];
+    const unsigned long long v1 = (long long)b + 1 < a.nblocks ? a.woff[2 * ((unsigned long long)b + 1)] : (unsigned long long)a.totals_a[0];
+    if (v0 == v1) return;
+  }
   const TMap tm = thread_map(g, b);
   // ---- A: active voxels per thread, exclusive scan (thread order == scan order) ----
   Quad q;

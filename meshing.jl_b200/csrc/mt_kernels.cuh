@@ -132,6 +132,13 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
   const TMap tm = thread_map(g, b);
   const int x = tm.x;
   if (g.ghost && x == 0) return;  // ghost row of an MT slab: its faces and vertices belong to the previous slab
+  {
+    // inclusive (vertex, face) prefixes of every block are in `status`: a block that adds no face has no active
+    // voxel (each one emits >= 1 face) -- leave before touching the bit-field (most blocks of a sparse field).
+    const unsigned long long f1 = a.status[2 * (unsigned long long)b + 1] & VAL_MASK;
+    const unsigned long long f0 = b > 0 ? (a.status[2 * (unsigned long long)(b - 1) + 1] & VAL_MASK) : 0ull;
+    if (f0 == f1) return;
+  }
   // ---- A: active voxels per thread, exclusive scan (thread order == scan order) ----
   uint32_t tna;
   {

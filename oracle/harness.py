@@ -69,7 +69,7 @@ def _field(sdf):
 def isosurface(sdf, algo=MC, iso=0.0, iso_is_f32=False, eps=1e-3, eps_is_f32=False,
                ranges=None, range_kind=RANGE_INT, nthreads=1, xrange=None, copy=True):
     """Oracle isosurface.  `ranges` = ((x0,x1),(y0,y1),(z0,z1)) endpoints (default (-1,1)^3).
-    `xrange` = (xlo, xhi) restricts the MC sweep to voxel x-planes [xlo, xhi) (bounded bench sample; face
+    `xrange` = (xlo, xhi) restricts the sweep to voxel x-planes [xlo, xhi) (bounded bench sample; face
     indices are then relative to the first vertex of the range).  `copy=False` returns only the counts.
     Returns (vertices[nv,3] float32|float64, faces[nf,3] int64 1-based)."""
     a = sdf if (isinstance(sdf, np.ndarray) and sdf.flags.f_contiguous) else _field(sdf)

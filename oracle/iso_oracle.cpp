@@ -274,21 +274,51 @@ struct MTState {
 
 template <class T, class I, class E, class P, class V>
 void run_mt(const T* sdf, int64_t nx, int64_t ny, int64_t nz, I iso, E eps, double x0, double x1, double y0,
-            double y1, double z0, double z1, Result& out) {
+            double y1, double z0, double z1, int nthreads, int64_t xlo, int64_t xhi, Result& out) {
   out.vert_is_f64 = std::is_same<V, double>::value;
-  MTState<T, I, E, P, V> st{sdf, nx, ny, nz, iso, eps, LinRange<P>(x0, x1, nx), LinRange<P>(y0, y1, ny),
-                            LinRange<P>(z0, z1, nz), {}, &verts_of<V>(out), &out.faces};
-  const int64_t sx = 1, sy = nx, sz = nx * ny;
-  for (int64_t i = 0; i < nx - 1; ++i)
-    for (int64_t j = 0; j < ny - 1; ++j)
-      for (int64_t k = 0; k < nz - 1; ++k) {
-        const T* p = sdf + i * sx + j * sy + k * sz;
-        // corner order :146-153
-        T vals[8] = {p[0], p[sy], p[sx + sy], p[sx], p[sz], p[sy + sz], p[sx + sy + sz], p[sx + sz]};
-        uint8_t c = get_cubeindex(vals, iso);
-        if (no_triangles(c)) continue;
-        st.procVox(vals, i + 1, j + 1, k + 1, c);
-      }
+  if (nx < 2 || ny < 2 || nz < 2) return;
+  // [xlo, xhi): voxel x-planes to sweep (bench: a bounded sample of a large field); the whole volume is [0, nx-1)
+  if (xlo < 0) xlo = 0;
+  if (xhi < 0 || xhi > nx - 1) xhi = nx - 1;
+  if (xhi <= xlo) return;
+  auto sweep = [&](int64_t xa, int64_t xb, Result& r) {
+    r.vert_is_f64 = out.vert_is_f64;
+    MTState<T, I, E, P, V> st{sdf, nx, ny, nz, iso, eps, LinRange<P>(x0, x1, nx), LinRange<P>(y0, y1, ny),
+                              LinRange<P>(z0, z1, nz), {}, &verts_of<V>(r), &r.faces};
+    const int64_t sx = 1, sy = nx, sz = nx * ny;
+    for (int64_t i = xa; i < xb; ++i)
+      for (int64_t j = 0; j < ny - 1; ++j)
+        for (int64_t k = 0; k < nz - 1; ++k) {
+          const T* p = sdf + i * sx + j * sy + k * sz;
+          // corner order :146-153
+          T vals[8] = {p[0], p[sy], p[sx + sy], p[sx], p[sz], p[sy + sz], p[sx + sy + sz], p[sx + sz]};
+          uint8_t c = get_cubeindex(vals, iso);
+          if (no_triangles(c)) continue;
+          st.procVox(vals, i + 1, j + 1, k + 1, c);
+        }
+  };
+  if (nthreads <= 1) {
+    sweep(xlo, xhi, out);
+    return;
+  }
+  // x-slab threaded driver (bench CPU arm only, a THROUGHPUT measure): every thread sweeps its x-range with its own
+  // vertex dictionary, so vertices on slab boundaries are duplicated -- not the reference's mesh, never used for parity.
+  int64_t nvx = xhi - xlo;
+  if (nthreads > nvx) nthreads = (int)nvx;
+  std::vector<Result> parts(nthreads);
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t) {
+    int64_t xa = xlo + nvx * t / nthreads, xb = xlo + nvx * (t + 1) / nthreads;
+    th.emplace_back([&, t, xa, xb] { sweep(xa, xb, parts[t]); });
+  }
+  for (auto& t : th) t.join();
+  std::vector<V>& vts = verts_of<V>(out);
+  for (int t = 0; t < nthreads; ++t) {
+    int64_t base = (int64_t)(vts.size() / 3);
+    std::vector<V>& pv = verts_of<V>(parts[t]);
+    vts.insert(vts.end(), pv.begin(), pv.end());
+    for (int64_t f : parts[t].faces) out.faces.push_back(f + base);
+  }
 }
 
 // ---- type dispatch ------------------------------------------------------------------------------------
@@ -306,7 +336,7 @@ struct Args {
   double x0, x1, y0, y1, z0, z1;
   int range_kind;
   int nthreads;
-  int64_t xlo, xhi;  // MC only: voxel x-plane range, -1 = whole volume
+  int64_t xlo, xhi;  // voxel x-plane range of the sweep, -1 = whole volume (bench samples)
 };
 
 template <class T, class I, class E, class P>
@@ -322,9 +352,9 @@ void dispatch_v(const Args& a, Result& out) {
       run_mc<T, I, P, float>((const T*)a.sdf, a.nx, a.ny, a.nz, (I)a.iso, a.x0, a.x1, a.y0, a.y1, a.z0, a.z1, a.nthreads, a.xlo, a.xhi, out);
   } else {
     if (f64)
-      run_mt<T, I, E, P, double>((const T*)a.sdf, a.nx, a.ny, a.nz, (I)a.iso, (E)a.eps, a.x0, a.x1, a.y0, a.y1, a.z0, a.z1, out);
+      run_mt<T, I, E, P, double>((const T*)a.sdf, a.nx, a.ny, a.nz, (I)a.iso, (E)a.eps, a.x0, a.x1, a.y0, a.y1, a.z0, a.z1, a.nthreads, a.xlo, a.xhi, out);
     else
-      run_mt<T, I, E, P, float>((const T*)a.sdf, a.nx, a.ny, a.nz, (I)a.iso, (E)a.eps, a.x0, a.x1, a.y0, a.y1, a.z0, a.z1, out);
+      run_mt<T, I, E, P, float>((const T*)a.sdf, a.nx, a.ny, a.nz, (I)a.iso, (E)a.eps, a.x0, a.x1, a.y0, a.y1, a.z0, a.z1, a.nthreads, a.xlo, a.xhi, out);
   }
 }
 template <class T, class I, class E>

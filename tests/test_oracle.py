@@ -176,3 +176,19 @@ def test_nan_samples_are_outside(oracle):
     assert ((c != 0xFF).sum()) == 8  # NaN < iso is false -> 8 voxels see one "outside" corner
     v, f = oracle.isosurface(s, oracle.MC, iso_is_f32=True)
     assert len(f) == 8 and np.isnan(v).any()
+
+
+def test_mt_xrange_sample_is_the_same_sweep(oracle, pkg):
+    """bench.py times the MT restatement on a bounded x-range: the full range must be the full sweep, and a partial
+    range the sweep of that sub-volume (first-touch order restarts at the range's first plane)."""
+    s = pkg.synth.gyroid((20, 14, 17))
+    v, f = oracle.isosurface(s, oracle.MT, iso_is_f32=True, eps_is_f32=True)
+    v1, f1 = oracle.isosurface(s, oracle.MT, iso_is_f32=True, eps_is_f32=True, xrange=(0, 19))
+    assert np.array_equal(f, f1) and np.array_equal(v, v1)
+    # planes [0, 7) of the volume == the whole sweep of the first 8 sample planes
+    v2, f2 = oracle.isosurface(s, oracle.MT, iso_is_f32=True, eps_is_f32=True, xrange=(0, 7), ranges=((0, 19), (0, 1), (0, 1)))
+    v3, f3 = oracle.isosurface(np.asfortranarray(s[:8]), oracle.MT, iso_is_f32=True, eps_is_f32=True, ranges=((0, 7), (0, 1), (0, 1)))
+    assert np.array_equal(f2, f3) and np.allclose(v2, v3, atol=1e-5)
+    # threaded throughput driver: same faces count, boundary vertices duplicated (never used for parity)
+    v4, f4 = oracle.isosurface(s, oracle.MT, iso_is_f32=True, eps_is_f32=True, nthreads=3)
+    assert len(f4) == len(f) and len(v4) >= len(v)
