@@ -82,7 +82,8 @@ struct b200iso_handle {
   DevBuf<uint32_t> bits;
   DevBuf<uint32_t> celloff;      // MT: per-cell vertex prefix inside its block
   DevBuf<unsigned long long> status;
-  DevBuf<unsigned long long> woff;  // MC: exclusive (vertex, face) prefix of every generate block
+  DevBuf<unsigned long long> woff;  // MC: exclusive (vertex, face) prefix of every generate block; MT (split count): raw block totals
+  DevBuf<unsigned long long> chain2;  // MT (split count): look-back state of the scan blocks
   long long chain_blocks = 0;       // blocks of the look-back chain of the last count
   DevBuf<double> coords;
   DevBuf<unsigned char> field;   // staging of a host field
@@ -235,7 +236,19 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
   } else if (p->algo == B200ISO_MC)
     iso::mc_count_warp_kernel<<<(unsigned)h->chain_blocks, iso::WC_THREADS, 0, st>>>(h->bits.p, g, h->nblocks, h->status.p, h->ticket,
                                                                                    h->chain_blocks, h->totals_dev, totals_out, h->woff.p);
-  else
+  else if (h->split_count) {
+    // MT, split form: raw block totals -> light look-back scan into the inclusive prefixes generate reads
+    const long long per = (long long)iso::SC_THREADS * iso::SC_PER, nsb = (h->nblocks + per - 1) / per;
+    if (int rc = h->woff.reserve((size_t)h->nblocks * 2)) return rc;
+    if (int rc = h->chain2.reserve((size_t)nsb * 2)) return rc;
+    CU(cudaMemsetAsync(h->chain2.p, 0, (size_t)nsb * 2 * sizeof(unsigned long long), st));
+    iso::count_kernel<1><<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->status.p, h->ticket, h->nblocks, h->totals_dev, totals_out,
+                                                                           h->celloff.p, h->woff.p);
+    CU(cudaGetLastError());
+    h->launches++;
+    iso::mt_scan_blocks_kernel<<<(unsigned)nsb, iso::SC_THREADS, 0, st>>>(h->woff.p, h->nblocks, h->status.p, h->chain2.p, h->ticket, nsb,
+                                                                          g.ghost ? (long long)g.blocks_per_row - 1 : -1LL, h->totals_dev, totals_out);
+  } else
     iso::count_kernel<1><<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->status.p, h->ticket, h->nblocks, h->totals_dev, totals_out, h->celloff.p);
   CU(cudaGetLastError());
   h->launches++;
@@ -345,7 +358,7 @@ int b200iso_destroy(b200iso_handle* h) {
   h->vstage1.release(), h->fstage1.release();
   for (cudaEvent_t e : h->slab_ev) cudaEventDestroy(e);
   h->pool.release();
-  h->bits.release(), h->celloff.release(), h->woff.release(), h->status.release(), h->coords.release(), h->field.release(), h->vstage.release(), h->fstage.release();
+  h->bits.release(), h->celloff.release(), h->woff.release(), h->chain2.release(), h->status.release(), h->coords.release(), h->field.release(), h->vstage.release(), h->fstage.release();
   if (h->ticket) cudaFree(h->ticket);
   if (h->totals_dev) cudaFree(h->totals_dev);
   if (h->totals_host) cudaFreeHost(h->totals_host);

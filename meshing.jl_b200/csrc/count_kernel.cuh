@@ -17,12 +17,15 @@ namespace iso {
 template <int ALGO>
 __global__ void __launch_bounds__(CB_THREADS)
 count_kernel(const uint32_t* __restrict__ bits, Grid g, unsigned long long* status, unsigned int* ticket,
-             long long nblocks, long long* totals_a, long long* totals_b, uint32_t* __restrict__ celloff) {
+             long long nblocks, long long* totals_a, long long* totals_b, uint32_t* __restrict__ celloff,
+             unsigned long long* __restrict__ raw = nullptr) {
   __shared__ uint8_t nf_s[256];
   __shared__ uint32_t s_w[CB_THREADS / 32];
   __shared__ uint32_t red_v[CB_THREADS / 32], red_f[CB_THREADS / 32];
   __shared__ unsigned sb;
-  if (threadIdx.x == 0) sb = atomicAdd(ticket, 1u);
+  // raw != nullptr: split form -- store the block's (vertex, face) totals, mt_scan_blocks_kernel scans them afterwards
+  // (no chain over the counting blocks: see the note at mc_count_chunks_kernel)
+  if (threadIdx.x == 0) sb = raw ? blockIdx.x : atomicAdd(ticket, 1u);
   for (int i = threadIdx.x; i < 256; i += CB_THREADS) nf_s[i] = ALGO == 0 ? (uint8_t)((ISO_MC_VERTS[i] >> 52) & 7) : ISO_MT_NF[i];
   __syncthreads();
   const unsigned b = sb;
@@ -70,6 +73,10 @@ count_kernel(const uint32_t* __restrict__ bits, Grid g, unsigned long long* stat
     unsigned long long av = 0, af = 0;
 #pragma unroll
     for (int w = 0; w < CB_THREADS / 32; ++w) av += red_v[w], af += red_f[w];
+    if (raw) {
+      if (threadIdx.x == 0) raw[2 * (unsigned long long)b] = av, raw[2 * (unsigned long long)b + 1] = af;
+      return;
+    }
     unsigned long long ev, ef;
     lookback(status, (long long)b, av, af, ev, ef);
     if ((long long)b == nblocks - 1 && threadIdx.x == 0) {
@@ -271,6 +278,72 @@ mc_scan_chunks_kernel(unsigned long long* __restrict__ woff, long long nchunks, 
   for (int k = 0; k < SC_PER; ++k) {
     if (i0 + k < nchunks) woff[2 * (i0 + k)] = pv, woff[2 * (i0 + k) + 1] = pf;
     pv += v[k], pf += f[k];
+  }
+}
+
+
+// MT: scans the raw block totals into the INCLUSIVE prefixes mt_generate_kernel reads (`status`, FLAG_INC | value per
+// word, one pair per counting block); `chain` is the look-back state of the scan blocks themselves.  The last scan
+// block writes the totals, minus the ghost row of an MT slab (its prefix ends at block blocks_per_row - 1).
+__global__ void __launch_bounds__(SC_THREADS)
+mt_scan_blocks_kernel(const unsigned long long* __restrict__ raw, long long nblocks, unsigned long long* status,
+                      unsigned long long* chain, unsigned int* ticket, long long nsb, long long ghost_block, long long* totals_a,
+                      long long* totals_b) {
+  __shared__ unsigned long long wsum_v[SC_THREADS / 32], wsum_f[SC_THREADS / 32];
+  __shared__ unsigned long long base_s[2];
+  __shared__ unsigned sb;
+  if (threadIdx.x == 0) sb = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const long long b = sb;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long i0 = (b * SC_THREADS + threadIdx.x) * SC_PER;
+  unsigned long long v[SC_PER], f[SC_PER], tv = 0, tf = 0;
+#pragma unroll
+  for (int k = 0; k < SC_PER; ++k) {
+    const bool in = i0 + k < nblocks;
+    v[k] = in ? raw[2 * (i0 + k)] : 0ull, f[k] = in ? raw[2 * (i0 + k) + 1] : 0ull;
+    tv += v[k], tf += f[k];
+  }
+  unsigned long long iv = tv, jf = tf;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long a = __shfl_up_sync(0xffffffffu, iv, o), c = __shfl_up_sync(0xffffffffu, jf, o);
+    if (lane >= o) iv += a, jf += c;
+  }
+  if (lane == 31) wsum_v[w] = iv, wsum_f[w] = jf;
+  __syncthreads();
+  unsigned long long wbv = 0, wbf = 0, av = 0, af = 0;
+#pragma unroll
+  for (int k = 0; k < SC_THREADS / 32; ++k) {
+    if (k < w) wbv += wsum_v[k], wbf += wsum_f[k];
+    av += wsum_v[k], af += wsum_f[k];
+  }
+  if (w == 0) {
+    unsigned long long ev, ef;
+    lookback(chain, b, av, af, ev, ef);
+    if (lane == 0) base_s[0] = ev, base_s[1] = ef;
+  }
+  __syncthreads();
+  unsigned long long pv = base_s[0] + wbv + (iv - tv), pf = base_s[1] + wbf + (jf - tf);
+#pragma unroll
+  for (int k = 0; k < SC_PER; ++k) {
+    pv += v[k], pf += f[k];
+    if (i0 + k < nblocks) {
+      st_relaxed(status + 2 * (i0 + k), FLAG_INC | pv);
+      st_relaxed(status + 2 * (i0 + k) + 1, FLAG_INC | pf);
+    }
+  }
+  if (b == nsb - 1 && threadIdx.x == 0) {
+    unsigned long long gv = 0, gf = 0;
+    if (ghost_block >= 0) {  // written by a scan block with a lower (or this) ticket: it is running or done
+      unsigned long long sv, sf;
+      do {
+        sv = ld_relaxed(status + 2 * ghost_block), sf = ld_relaxed(status + 2 * ghost_block + 1);
+      } while ((sv >> 62) != 2 || (sf >> 62) != 2);
+      gv = sv & VAL_MASK, gf = sf & VAL_MASK;
+    }
+    totals_a[0] = (long long)(base_s[0] + av - gv), totals_a[1] = (long long)(base_s[1] + af - gf);
+    if (totals_b) totals_b[0] = totals_a[0], totals_b[1] = totals_a[1];
   }
 }
 
