@@ -173,6 +173,7 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
   g.ghost = p->algo == B200ISO_MT && p->x_ghost != 0 ? 1 : 0;
   h->nblocks = (nx > 1 && ny > 1 && nz > 1) ? (long long)(nx - 1) * g.blocks_per_row : 0;
 
+  if (h->nblocks >= (1ll << 31)) return fail(B200ISO_EINVAL, "grid too large: %lld generate blocks (limit 2^31)", h->nblocks);
   if (h->nblocks == 0) {  // a dimension < 2: zero voxels, empty mesh (src/marching_cubes.jl:40)
     CU(cudaMemsetAsync(h->totals_dev, 0, 2 * sizeof(long long), st));
     if (totals_out) CU(cudaMemsetAsync(totals_out, 0, 2 * sizeof(long long), st));

@@ -136,7 +136,7 @@ mc_count_warp_kernel(const uint32_t* __restrict__ bits, Grid g, long long nchunk
     for (int q0 = q_lo; q0 < q_lo + CB_THREADS && q0 < g.quads_per_row; q0 += 32) {
       TMap tm;
       const int qr = q0 + lane;
-      tm.x = x, tm.y = qr / g.Wq, tm.zq = qr - tm.y * g.Wq, tm.live = qr < g.quads_per_row;
+      tm.x = x, tm.y = (int)fast_div((unsigned)qr, g.wq_mul, g.wq_sh), tm.zq = qr - tm.y * g.Wq, tm.live = qr < g.quads_per_row;
       Quad q;
       if (tm.live && load_quad(bits, g, tm.x, tm.y, tm.zq, q)) {
 #pragma unroll
@@ -201,7 +201,7 @@ mc_count_chunks_kernel(const uint32_t* __restrict__ bits, Grid g, long long nchu
   const int q_lo = (int)(chunk - (long long)x * g.blocks_per_row) * CB_THREADS;
   for (int q0 = q_lo; q0 < q_lo + CB_THREADS && q0 < g.quads_per_row; q0 += 32) {
     const int qr = q0 + lane;
-    const int y = qr / g.Wq, zq = qr - y * g.Wq;
+    const int y = (int)fast_div((unsigned)qr, g.wq_mul, g.wq_sh), zq = qr - y * g.Wq;
     Quad q;
     if (qr < g.quads_per_row && load_quad(bits, g, x, y, zq, q)) {
 #pragma unroll

@@ -129,7 +129,7 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
   for (int i = tid; i < 160; i += CB_THREADS) eshift_s[i] = ISO_MT_EDGE_SHIFT[i];
 
   const unsigned b = blockIdx.x;
-  const TMap tm = thread_map(g, b);
+  const TMap tm = thread_map_div(g, b);
   const int x = tm.x;
   if (g.ghost && x == 0) return;  // ghost row of an MT slab: its faces and vertices belong to the previous slab
   {
