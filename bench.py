@@ -210,7 +210,7 @@ def run_reference(args, rank):
     oracle.build()
     pkg = load_package()
     spec = workload_spec(args.workload, args.n, 1)
-    threads = 1 if spec["algo"] == "MT" else (os.cpu_count() or 1)
+    threads = os.cpu_count() or 1  # (MT: every x-slab thread keeps its own vertex dictionary -- a throughput measure)
     nx, ny, nz = spec["shape"]
     per_plane = (ny - 1) * (nz - 1)
     # size the per-step sample: probe one batch of planes, then aim for ~2 s per step
