@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <limits>
 
 #include "iso_kernels.cuh"
@@ -472,7 +473,7 @@ int b200iso_totals(b200iso_handle* h, int64_t* nverts, int64_t* nfaces, int* ver
   return 0;
 }
 
-int b200iso_count(b200iso_handle* h, const b200iso_params* p, const void* sdf, int mem, int64_t nx, int64_t ny, int64_t nz,
+static int b200iso_count_impl(b200iso_handle* h, const b200iso_params* p, const void* sdf, int mem, int64_t nx, int64_t ny, int64_t nz,
                   int64_t ldx, int64_t* nverts, int64_t* nfaces, int* vert_is_f64) {
   if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
   if (int rc = check_params(p, nx, ny, nz, ldx)) return rc;
@@ -518,7 +519,18 @@ int b200iso_count(b200iso_handle* h, const b200iso_params* p, const void* sdf, i
   return 0;
 }
 
-int b200iso_generate(b200iso_handle* h, void* verts, int64_t* faces, int mem, int64_t vertex_base) {
+int b200iso_count(b200iso_handle* h, const b200iso_params* p, const void* sdf, int mem, int64_t nx, int64_t ny, int64_t nz,
+                  int64_t ldx, int64_t* nverts, int64_t* nfaces, int* vert_is_f64) {
+  try {
+    return b200iso_count_impl(h, p, sdf, mem, nx, ny, nz, ldx, nverts, nfaces, vert_is_f64);
+  } catch (const std::exception& e) {  // (std::bad_alloc, std::system_error from a thread): nothing may cross the C ABI
+    return fail(B200ISO_ENOMEM, "b200iso_count: %s", e.what());
+  } catch (...) {
+    return fail(B200ISO_ENOMEM, "b200iso_count: unknown C++ exception");
+  }
+}
+
+static int b200iso_generate_impl(b200iso_handle* h, void* verts, int64_t* faces, int mem, int64_t vertex_base) {
   if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
   if (mem != B200ISO_HOST && mem != B200ISO_DEVICE) return fail(B200ISO_EINVAL, "bad mem kind %d", mem);
   CU(cudaSetDevice(h->device));
@@ -559,6 +571,16 @@ int b200iso_generate(b200iso_handle* h, void* verts, int64_t* faces, int mem, in
   return 0;
 }
 
+int b200iso_generate(b200iso_handle* h, void* verts, int64_t* faces, int mem, int64_t vertex_base) {
+  try {
+    return b200iso_generate_impl(h, verts, faces, mem, vertex_base);
+  } catch (const std::exception& e) {  // (std::bad_alloc, std::system_error from a thread): nothing may cross the C ABI
+    return fail(B200ISO_ENOMEM, "b200iso_generate: %s", e.what());
+  } catch (...) {
+    return fail(B200ISO_ENOMEM, "b200iso_generate: unknown C++ exception");
+  }
+}
+
 // One-shot host form: x-slab software pipeline over three streams.  x is the scan-outermost
 // axis, so the mesh of voxel rows [a, b) is a contiguous piece of the output and needs sample planes [a, b] only:
 //   in_stream : strided (2-D) H2D copies of the slabs, all enqueued up front (>= 256 B rows run at full PCIe rate)
@@ -567,7 +589,7 @@ int b200iso_generate(b200iso_handle* h, void* verts, int64_t* faces, int mem, in
 //               overlapping the H2D of the slabs behind it (PCIe is full duplex)
 // Every slab is the sharded sub-problem of api.isosurface_slab (x_offset / nx_global / vertex base; Marching
 // Tetrahedra slabs carry their ghost row), so the concatenation is byte-identical to the unsharded mesh.
-int b200iso_extract_host(b200iso_handle* h, const b200iso_params* p, const void* sdf, int64_t nx, int64_t ny, int64_t nz,
+static int b200iso_extract_host_impl(b200iso_handle* h, const b200iso_params* p, const void* sdf, int64_t nx, int64_t ny, int64_t nz,
                          int64_t ldx, void* verts, int64_t vcap, int64_t* faces, int64_t fcap, int64_t* nverts,
                          int64_t* nfaces, int* vert_is_f64) {
   if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
@@ -671,6 +693,18 @@ int b200iso_extract_host(b200iso_handle* h, const b200iso_params* p, const void*
   if (nfaces) *nfaces = cf;
   if (overflow) return fail(B200ISO_ECAPACITY, "mesh has %lld vertices / %lld faces, capacity is %lld / %lld", (long long)cv, (long long)cf, (long long)vcap, (long long)fcap);
   return 0;
+}
+
+int b200iso_extract_host(b200iso_handle* h, const b200iso_params* p, const void* sdf, int64_t nx, int64_t ny, int64_t nz,
+                         int64_t ldx, void* verts, int64_t vcap, int64_t* faces, int64_t fcap, int64_t* nverts,
+                         int64_t* nfaces, int* vert_is_f64) {
+  try {
+    return b200iso_extract_host_impl(h, p, sdf, nx, ny, nz, ldx, verts, vcap, faces, fcap, nverts, nfaces, vert_is_f64);
+  } catch (const std::exception& e) {  // (std::bad_alloc, std::system_error from a thread): nothing may cross the C ABI
+    return fail(B200ISO_ENOMEM, "b200iso_extract_host: %s", e.what());
+  } catch (...) {
+    return fail(B200ISO_ENOMEM, "b200iso_extract_host: unknown C++ exception");
+  }
 }
 
 int b200iso_case_indices(b200iso_handle* h, uint8_t* out, int mem) {

@@ -123,7 +123,7 @@ struct Uploader {
     for (auto& a : issued) a.store(0);
     for (int t = 0; t < T; ++t)
       if (cudaError_t e = cudaStreamWaitEvent(pool->in[t].stream, after, 0)) return e;
-    for (int t = 0; t < T; ++t) {
+    for (int t = 0; t < T; ++t) try {
       threads.emplace_back([=]() {
         Pool::Lane& L = pool->in[t];
         cudaError_t e = cudaSetDevice(pool->device);
@@ -158,6 +158,10 @@ struct Uploader {
           issued[t].store(k + 1, std::memory_order_release);  // always advances: the consumer never waits forever
         }
       });
+    } catch (...) {  // thread creation failed: no exception may cross the C ABI; unstarted lanes count as failed
+      err.store((int)cudaErrorUnknown);
+      for (int u = t; u < T; ++u) issued[u].store(S, std::memory_order_release);
+      return cudaErrorUnknown;
     }
     return cudaSuccess;
   }
@@ -206,7 +210,7 @@ struct Downloader {
     for (int t = 0; t < T; ++t)
       if (cudaError_t e = cudaStreamWaitEvent(pool->out[t].stream, after, 0)) return e;
     if (pinned) return cudaSuccess;  // direct DMA from the calling thread, no workers
-    for (int t = 0; t < T; ++t) {
+    for (int t = 0; t < T; ++t) try {
       threads.emplace_back([=]() {
         Pool::Lane& L = pool->out[t];
         cudaError_t e = cudaSetDevice(pool->device);
@@ -239,6 +243,10 @@ struct Downloader {
           drained[t].store(k + 1, std::memory_order_release);
         }
       });
+    } catch (...) {  // thread creation failed: stop the lanes that did start
+      err.store((int)cudaErrorUnknown);
+      closed.store(true, std::memory_order_release);
+      return cudaErrorUnknown;
     }
     return cudaSuccess;
   }
