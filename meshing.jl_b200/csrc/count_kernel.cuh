@@ -188,7 +188,8 @@ mc_count_warp_kernel(const uint32_t* __restrict__ bits, Grid g, long long nchunk
 // that costs more than the counting.  Split: (a) every warp counts its chunk and stores the raw pair -- no chain, no
 // ticket, no barrier; (b) a single-pass decoupled look-back scan over the stored pairs, whose blocks are uniform
 // and tiny (1024 pairs each), turns them into exclusive prefixes in place.
-__global__ void __launch_bounds__(WC_THREADS)
+// (launch bound 6 blocks/SM = 40 registers, 75 % occupancy: 0.171 ms against 0.174 at 5 and 0.179 at 4 blocks/SM)
+__global__ void __launch_bounds__(WC_THREADS, 6)
 mc_count_chunks_kernel(const uint32_t* __restrict__ bits, Grid g, long long nchunks, unsigned long long* __restrict__ woff) {
   __shared__ uint8_t nf_s[256];
   nf_s[threadIdx.x] = (uint8_t)((ISO_MC_VERTS[threadIdx.x] >> 52) & 7);
