@@ -20,4 +20,29 @@ for m in (pkg.MarchingCubes(iso=F(0)), pkg.MarchingTetrahedra(iso=F(0), eps=F(1e
         xa, xb = pkg.sharding.slab_bounds(41, 3, r, ghost=gh)
         v, f = pkg.api.isosurface_slab(s[xa:xb], m, xa, 41, 100)
         print("slab", r, len(v), len(f))
+# one-shot host path (slab pipeline, pinned staging threads) and the fused single pass
+import os as _os
+_os.environ["B200ISO_HOST_SLABS"] = "3"
+s = pkg.synth.gyroid((70, 33, 41))
+for m in (pkg.MarchingCubes(iso=F(0)), pkg.MarchingTetrahedra(iso=F(0), eps=F(1e-3))):
+    v0, f0 = pkg.isosurface(s, m)
+    v1, f1 = pkg.isosurface(s, m, capacity=(len(v0), len(f0)))
+    assert np.array_equal(f0, f1)
+    print("extract_host", type(m).__name__, len(v1), len(f1))
+# peer exchange: two handles as two ranks on one device
+import torch
+bufs = [torch.zeros(pkg.capi.PEER_BYTES // 8, dtype=torch.int64, device="cuda") for _ in range(2)]
+hs = [pkg.capi.Handle(0) for _ in range(2)]
+t = torch.from_numpy(np.ascontiguousarray(pkg.synth.gyroid((30, 20, 40)).transpose(2, 1, 0))).cuda().permute(2, 1, 0)
+p = pkg.api.make_params(pkg.MarchingCubes(iso=F(0)))
+bases = [torch.zeros(4, dtype=torch.int64, device="cuda") for _ in range(2)]
+torch.cuda.synchronize()
+for r, h in enumerate(hs):
+    h.set_peer_exchange(r, 2, [b.data_ptr() for b in bufs])
+for ep in range(2):
+    for h in hs:
+        h.count_async(p, t.data_ptr(), 30, 20, 40, t.stride(1))
+    for r, h in enumerate(hs):
+        h.exchange_async(bases[r].data_ptr())
+    print("peer", ep, [h.totals()[:2] for h in hs], [int(b[0]) for b in bases])
 print("done")
