@@ -681,7 +681,16 @@ struct FieldOf<3> {
 template <int MODE, typename V, bool FUSED>
 __global__ void __launch_bounds__(CB_THREADS, ISO_GEN_MINB)
 mc_generate_kernel(GenArgs a, Grid g) {
-  __shared__ unsigned long long tabV[256], tabF[256];
+// per-case tables straight from global memory through L1 (4 KB, hot in every SM): staging them in shared memory
+// per block cost more than it saved (generate 0.741 -> 0.726 ms at 1024^3); -DISO_GEN_SMEM_TABLES restores the staging
+#ifndef ISO_GEN_SMEM_TABLES
+#define tabV(i) __ldg(&ISO_MC_VERTS[i])
+#define tabF(i) __ldg(&ISO_MC_FACES[i])
+#else
+  __shared__ unsigned long long tabV_s[256], tabF_s[256];
+#define tabV(i) tabV_s[i]
+#define tabF(i) tabF_s[i]
+#endif
   __shared__ unsigned long long s_base[2];
   __shared__ uint32_t s_w[CB_THREADS / 32];
   __shared__ unsigned s_b;
@@ -703,7 +712,11 @@ mc_generate_kernel(GenArgs a, Grid g) {
     const unsigned long long v1 = (long long)b + 1 < a.nblocks ? a.woff[2 * ((unsigned long long)b + 1)] : (unsigned long long)a.totals_a[0];
     if (v0 == v1) return;
   }
+#ifdef ISO_GEN_PLAIN_DIV
+  const TMap tm = thread_map_div(g, b);
+#else
   const TMap tm = thread_map(g, b);
+#endif
   // ---- A: active voxels per thread, exclusive scan (thread order == scan order) ----
   Quad q;
   const uint32_t tna = count_active(a.bits, g, tm, q);
@@ -716,7 +729,9 @@ mc_generate_kernel(GenArgs a, Grid g) {
     }
     return;
   }
-  for (int i = tid; i < 256; i += CB_THREADS) tabV[i] = ISO_MC_VERTS[i], tabF[i] = ISO_MC_FACES[i];
+#ifdef ISO_GEN_SMEM_TABLES
+  for (int i = tid; i < 256; i += CB_THREADS) tabV_s[i] = ISO_MC_VERTS[i], tabF_s[i] = ISO_MC_FACES[i];
+#endif
   if (tid < 12) edge_c[tid] = ISO_MC_EDGE_CORNERS[tid];
 
   unsigned long long bv = 0, bf = 0;
@@ -733,7 +748,7 @@ mc_generate_kernel(GenArgs a, Grid g) {
       if (tna && my_a0 < hi && my_a0 + tna > lo) push_records<0>(q, tm, my_a0, lo, hi, rec_yz, rec_c);
       __syncthreads();
       for (uint32_t s = tid; s < hi - lo; s += CB_THREADS) {
-        const unsigned long long t = tabV[rec_c[s]];
+        const unsigned long long t = tabV(rec_c[s]);
         tv += (uint32_t)((t >> 48) & 15), tf += (uint32_t)((t >> 52) & 7);
       }
       __syncthreads();
@@ -761,11 +776,11 @@ mc_generate_kernel(GenArgs a, Grid g) {
     const uint32_t r0 = 2 * tid, r1 = r0 + 1;
     uint32_t nv0 = 0, nf0 = 0, nv1 = 0, nf1 = 0;
     if (r0 < cnt) {
-      const unsigned long long tv = tabV[rec_c[r0]];
+      const unsigned long long tv = tabV(rec_c[r0]);
       nv0 = (uint32_t)((tv >> 48) & 15), nf0 = (uint32_t)((tv >> 52) & 7);
     }
     if (r1 < cnt) {
-      const unsigned long long tv = tabV[rec_c[r1]];
+      const unsigned long long tv = tabV(rec_c[r1]);
       nv1 = (uint32_t)((tv >> 48) & 15), nf1 = (uint32_t)((tv >> 52) & 7);
     }
 #pragma unroll
@@ -825,7 +840,7 @@ mc_generate_kernel(GenArgs a, Grid g) {
       const uint32_t s = owner_v[k];  // record index 0..255
       const uint32_t pk = rec_pk[s], yz = rec_yz[s];
       const uint32_t which = k - ((pk >> 8) & 0xfffu);
-      const uint32_t e = (uint32_t)(tabV[pk & 0xffu] >> (4 * which)) & 15u;
+      const uint32_t e = (uint32_t)(tabV(pk & 0xffu) >> (4 * which)) & 15u;
       const uint32_t cc = edge_c[e];
       const uint32_t ca = cc & 15u, cb = cc >> 4;
       // MC corner offsets (dx | dy<<1 | dz<<2) for corners 0..7: 0,1,3,2,4,5,7,6
@@ -853,7 +868,7 @@ mc_generate_kernel(GenArgs a, Grid g) {
     for (uint32_t k = tid; k < nfr; k += CB_THREADS) {
       const uint32_t pk = rec_pk[owner_f[k]];
       const uint32_t fi = k - (pk >> 20);
-      const uint32_t tri = (uint32_t)(tabF[pk & 0xffu] >> (12 * fi)) & 0xfffu;
+      const uint32_t tri = (uint32_t)(tabF(pk & 0xffu) >> (12 * fi)) & 0xfffu;
       const long long fct = vbase + (long long)bv + ((pk >> 8) & 0xfffu) + 1;  // 1-based index of the voxel's first vertex
       if (ffits || (long long)bf + k < a.fcap) {
         long long* o = a.faces + 3 * ((long long)bf + k);
@@ -864,6 +879,8 @@ mc_generate_kernel(GenArgs a, Grid g) {
     __syncthreads();
   }
 }
+#undef tabV
+#undef tabF
 
 // faces[0 .. 3*min(totals[1], fcap)) += *base   (sharded fix-up after the all-gather of the slab totals)
 __global__ void add_base_kernel(long long* __restrict__ faces, long long fcap, const long long* __restrict__ totals,
