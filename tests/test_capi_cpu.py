@@ -62,3 +62,22 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".jl", "Makefile")):
                 src = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in src.lower(), os.path.join(dp, f)
+
+
+def test_vertex_type_rule_of_the_host_mirror_matches_the_oracle(pkg, oracle):
+    """api._vert_is_f64 sizes the caller's arrays for the one-shot host call before anything ran: it must be the
+    reference's float(promote_type(...)) rule (src/marching_cubes.jl:31, src/marching_tetrahedra.jl:131)."""
+    api = pkg.api
+    s32 = pkg.synth.sphere((6, 6, 6))
+    for field in (s32, s32.astype(np.float64)):
+        for algo in ("MC", "MT"):
+            for f32 in (True, False):
+                for rk, conv in ((oracle.RANGE_INT, int), (oracle.RANGE_F32, np.float32), (oracle.RANGE_F64, float)):
+                    cv = api.Float32 if f32 else float
+                    m = api.MarchingCubes(iso=cv(0)) if algo == "MC" else api.MarchingTetrahedra(iso=cv(0), eps=cv(1e-3))
+                    rng = tuple((conv(-1), conv(1)) for _ in range(3))
+                    p = api.make_params(m, *rng)
+                    p.field_is_f64 = int(field.dtype == np.float64)
+                    v, _ = oracle.isosurface(field, 0 if algo == "MC" else 1, iso=0.0, iso_is_f32=f32, eps=1e-3, eps_is_f32=f32,
+                                             ranges=((-1, 1),) * 3, range_kind=rk)
+                    assert api._vert_is_f64(p) == (v.dtype == np.float64), (field.dtype, algo, f32, rk)

@@ -192,3 +192,17 @@ def test_mt_xrange_sample_is_the_same_sweep(oracle, pkg):
     # threaded throughput driver: same faces count, boundary vertices duplicated (never used for parity)
     v4, f4 = oracle.isosurface(s, oracle.MT, iso_is_f32=True, eps_is_f32=True, nthreads=3)
     assert len(f4) == len(f) and len(v4) >= len(v)
+
+
+def test_mt_sphere_is_a_closed_manifold(oracle, pkg):
+    """Marching Tetrahedra shares vertices through the reference's Dict: on a closed surface away from the volume
+    boundary every undirected edge of the mesh belongs to exactly two faces, with opposite orientations."""
+    s = pkg.synth.sphere((24, 25, 26))
+    v, f = oracle.isosurface(s, oracle.MT, iso_is_f32=True, eps_is_f32=True)
+    assert len(f) > 0 and f.min() == 1 and f.max() == len(v)
+    e = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+    und, cnt = np.unique(np.sort(e, axis=1), axis=0, return_counts=True)
+    assert (cnt == 2).all()
+    directed = {(int(a), int(b)) for a, b in e}
+    assert len(directed) == len(e) and all((b, a) in directed for a, b in directed)
+    assert len(v) - len(und) + len(f) == 2  # Euler characteristic of a sphere
