@@ -55,11 +55,14 @@ check(rc) = rc == 0 ? nothing : error("b200iso error $rc: $(last_error())")
 
 # one handle per thread (a handle is not thread-safe); created lazily on device B200ISO_DEVICE (default 0)
 const handles = Dict{Int,Ptr{Cvoid}}()
+const handles_lock = ReentrantLock()   # the Dict itself is shared between threads
 function handle()
-    get!(handles, Threads.threadid()) do
-        h = Ref{Ptr{Cvoid}}(C_NULL)
-        check(ccall((:b200iso_create, libb200iso), Cint, (Ref{Ptr{Cvoid}}, Cint), h, parse(Cint, get(ENV, "B200ISO_DEVICE", "0"))))
-        h[]
+    lock(handles_lock) do
+        get!(handles, Threads.threadid()) do
+            h = Ref{Ptr{Cvoid}}(C_NULL)
+            check(ccall((:b200iso_create, libb200iso), Cint, (Ref{Ptr{Cvoid}}, Cint), h, parse(Cint, get(ENV, "B200ISO_DEVICE", "0"))))
+            h[]
+        end
     end
 end
 
