@@ -29,3 +29,16 @@ def pkg():
     if not os.path.exists(lib):  # fresh checkout: build the CUDA library in-tree (nvcc cross-compiles without a GPU)
         subprocess.check_call(["make", "-C", os.path.join(PKG_DIR, "csrc")], stdout=subprocess.DEVNULL)
     return load_package()
+
+
+@pytest.fixture
+def c_example(pkg, tmp_path):
+    """examples/extract.c compiled as C99 against include/b200iso.h and linked with the built library."""
+    import subprocess
+    exe = str(tmp_path / "extract")
+    libdir = os.path.join(ROOT, "meshing.jl_b200", "lib")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-O2", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "extract.c"), "-o", exe, "-L" + libdir, "-lb200iso", "-lm", "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe

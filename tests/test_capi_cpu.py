@@ -81,3 +81,13 @@ def test_vertex_type_rule_of_the_host_mirror_matches_the_oracle(pkg, oracle):
                     v, _ = oracle.isosurface(field, 0 if algo == "MC" else 1, iso=0.0, iso_is_f32=f32, eps=1e-3, eps_is_f32=f32,
                                              ranges=((-1, 1),) * 3, range_kind=rk)
                     assert api._vert_is_f64(p) == (v.dtype == np.float64), (field.dtype, algo, f32, rk)
+
+
+def test_header_is_plain_c_and_the_c_example_links(pkg, c_example):
+    """include/b200iso.h must be usable from C (what ccall / cgo / JNI bind), not only from C++."""
+    import subprocess
+    exe = c_example
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "16"], capture_output=True, text=True)
+        assert r.returncode != 0 and "b200iso_create" in r.stderr  # no GPU: fails loudly, no fallback

@@ -609,3 +609,12 @@ def test_peer_exchange_timeout_reports_instead_of_hanging(pkg):
     h.set_peer_exchange(0, 0, None)
     h.count_async(p, t.data_ptr(), 20, 20, 20, t.stride(1))
     assert h.totals()[0] > 0  # the handle is usable again
+
+
+def test_c_example_runs_through_the_c_abi(pkg, c_example):
+    """examples/extract.c: plain C against include/b200iso.h -- two-phase and one-shot host calls, same bytes."""
+    import subprocess
+    exe = c_example
+    r = subprocess.run([exe, "96"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "identical bytes" in r.stdout
