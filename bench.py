@@ -33,6 +33,12 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
+# ONE metric string for both arms (--impl b200 / reference), every workload and every N: the driver pairs lines by it.
+# The workload, shape and method live in `config`.
+METRIC = "isosurface extraction throughput (Gvoxels/s; Mtriangles/s alongside)"
+UNIT = "Gvoxels/s"
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -235,10 +241,10 @@ def run_reference(args, rank):
     dt = (time.perf_counter() - t0) / args.steps
     value = planes * per_plane / dt / 1e9
     sample = f"voxel x-planes [0,{planes}) of the {nx}x{ny}x{nz} field ({planes * per_plane} voxels per step), full-field strides"
-    line = {"impl": "reference", "metric": "isosurface throughput, " + spec["desc"], "value": value, "unit": "Gvoxels/s",
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": spec.get("scaling", "weak"), "vs_baseline": None, "dtype": "f32 field, f64 positions, f32 vertices, int64 faces",
-            "data": "synthetic", "config": {"workload": args.workload, "shape": [nx, ny, nz], "sample": sample},
+            "data": "synthetic", "config": {"workload": args.workload, "description": spec["desc"], "shape": [nx, ny, nz], "sample": sample, "host_threads": threads},
             "cpu_baseline": {"value": value, "unit": "Gvoxels/s", "cores": threads, "kind": "port", "sample": sample,
                              "note": "C++ restatement of Meshing.jl's loops (oracle/iso_oracle.cpp); Julia is not installed"},
             "e2e": {"value": value, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -446,13 +452,13 @@ def main():
         bytes_step = 4.0 * nxl * ny * nz + vbytes * nv + 24 * nf  # rank 0's slab
         pipe_gbs = bytes_step / (ms_step * 1e-3) / 1e9
         line = {
-            "metric": "isosurface throughput (Gvoxels/s; Mtriangles/s alongside), " + spec["desc"],
-            "value": value, "unit": "Gvoxels/s", "mtriangles_per_s": mtri,
+            "metric": METRIC,
+            "value": value, "unit": UNIT, "mtriangles_per_s": mtri,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": spec.get("scaling", "weak"), "vs_baseline": None,
             "dtype": "f32 field, f64 positions, f32 vertices, int64 faces" if not f64 else "f32 field, f64 positions and vertices, int64 faces",
             "data": "synthetic",
-            "config": {"workload": args.workload, "shape": [nxg, ny, nz], "per_gpu_shape": [nxl, ny, nz], "algo": spec["algo"],
+            "config": {"workload": args.workload, "description": spec["desc"], "shape": [nxg, ny, nz], "per_gpu_shape": [nxl, ny, nz], "algo": spec["algo"],
                        "sharding": ("x-slabs + one 16-byte exchange of counts" if sharded else ("replicas" if world > 1 else "single GPU")),
                        "exchange": exchange,
                        "l2": "inputs larger than L2 (field %.2f GB per GPU, read once per step)" % (4.0 * nxl * ny * nz / 1e9),

@@ -88,6 +88,14 @@ int b200iso_version(void);
  * b200iso_use_own_stream switches back to the stream the handle created for itself. */
 int b200iso_set_stream(b200iso_handle* h, void* cuda_stream);
 int b200iso_use_own_stream(b200iso_handle* h);
+/* Which classify (sign-pack) kernel a count uses.  mode: -1 = automatic (TMA-staged on big 16-byte aligned Float32
+ * fields, per-lane loads otherwise; the default), 1 = TMA whenever the field can be described by a tensor map
+ * (Float32, base 16-byte aligned, ldx % 4 == 0), 0 = never TMA.  Results are identical; the parity tests use this
+ * to run every shape through both kernels.  The environment variable B200ISO_TMA=0|1 sets the initial mode.
+ * b200iso_classify_path reports what the last count actually ran (B200ISO_CLASSIFY_*, -1 before the first). */
+enum { B200ISO_CLASSIFY_LDG128 = 0, B200ISO_CLASSIFY_TMA = 1, B200ISO_CLASSIFY_SCALAR = 2, B200ISO_CLASSIFY_F64 = 3 };
+int b200iso_set_classify_mode(b200iso_handle* h, int mode);
+int b200iso_classify_path(b200iso_handle* h);
 
 /* ---- the drop-in pair: replaces the body of isosurface(sdf, method, X, Y, Z) ---------------------------
  * b200iso_count   : classify + count + scan.  `sdf` is Float32 (Float64 if p->field_is_f64), host or device (mem), nx*ny*nz samples with
@@ -116,24 +124,19 @@ int b200iso_generate_async(b200iso_handle* h, void* verts_dev, int64_t vcap, int
                            const int64_t* vertex_base_dev, int64_t vertex_base);
 int b200iso_totals(b200iso_handle* h, int64_t* nverts, int64_t* nfaces, int* vert_is_f64);
 
-/* ---- single-pass form (device-resident, capacity known up front) ----------------------------------------
- * b200iso_extract_async: the whole isosurface() in one enqueue -- classify, then ONE kernel that counts,
- *                        scans (decoupled look-back) and generates -- into device buffers of capacity
+/* ---- one-enqueue form (device-resident, capacity known up front) ----------------------------------------
+ * b200iso_extract_async: the whole isosurface() in one enqueue -- classify, count + scan, generate back to
+ *                        back on the handle's stream -- into device buffers of capacity
  *                        vcap vertices / fcap faces.  Elements beyond capacity are dropped, the true totals
  *                        are written to totals_dev (device int64[2], may be NULL) and kept for
  *                        b200iso_totals, so a caller that guessed too small re-allocates and calls again.
  *                        Face indices get vertex_base + (vertex_base_dev ? *vertex_base_dev : 0).
- *                        (Marching Tetrahedra runs its count and generate kernels back to back instead.)
  * b200iso_add_vertex_base_async: adds *vertex_base_dev to the first min(totals_dev[1], fcap) faces -- the
  *                        sharded fix-up when the slab's global vertex base (from the all-gather of the
  *                        slabs' totals) becomes known only after the slab was extracted. */
 int b200iso_extract_async(b200iso_handle* h, const b200iso_params* p, const void* sdf_dev, int64_t nx, int64_t ny,
                           int64_t nz, int64_t ldx, void* verts_dev, int64_t vcap, int64_t* faces_dev, int64_t fcap,
                           const int64_t* vertex_base_dev, int64_t vertex_base, int64_t* totals_dev);
-/* Strategy of b200iso_extract_async for Marching Cubes (results are identical):
- *   0 = (default) classify, count+scan, generate back to back -- the fastest measured form
- *   1 = classify, then ONE fused count/scan/generate kernel (decoupled look-back inside generate) */
-int b200iso_set_extract_mode(b200iso_handle* h, int mode);
 int b200iso_add_vertex_base_async(b200iso_handle* h, int64_t* faces_dev, int64_t fcap, const int64_t* totals_dev,
                                   const int64_t* vertex_base_dev);
 
@@ -148,11 +151,16 @@ int b200iso_add_vertex_base_async(b200iso_handle* h, int64_t* faces_dev, int64_t
  *                       bases_dev[0..3] = {vertex base, face base of this rank, total nverts, total nfaces};
  *                       all_dev (may be NULL) receives every rank's (nverts, nfaces).  Pass bases_dev as
  *                       vertex_base_dev to b200iso_generate_async.  Every rank must call it once per count (the
- *                       calls are matched by an epoch counter); a rank that never arrives makes the others fail
- *                       after about a second (B200ISO_ESTATE from b200iso_totals) instead of hanging. */
+ *                       calls are matched by an epoch counter).
+ * b200iso_set_peer_timeout: how long a rank waits for its peers inside b200iso_exchange_async: seconds (default 60:
+ *                       ordinary rank skew -- first-call allocations, data loading -- must not trip it); <= 0 waits
+ *                       for ever, like an NCCL collective.  After a time-out the generate kernels enqueued behind the
+ *                       exchange emit nothing, b200iso_totals returns B200ISO_ESTATE, and the exchange must be re-armed
+ *                       on ALL ranks (b200iso_set_peer_exchange with re-zeroed buffers) before it is used again. */
 #define B200ISO_PEER_MAX 16
 #define B200ISO_PEER_BYTES (2 * B200ISO_PEER_MAX * 4 * 8)
 int b200iso_set_peer_exchange(b200iso_handle* h, int rank, int world, void* const* slots);
+int b200iso_set_peer_timeout(b200iso_handle* h, double seconds);
 int b200iso_exchange_async(b200iso_handle* h, int64_t* bases_dev, int64_t* all_dev);
 
 /* ---- one-shot host form (host arrays in, host arrays out, capacity known up front) ----------------------

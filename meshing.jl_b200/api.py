@@ -64,17 +64,29 @@ def _range_kind(r, name):
             raise ValueError(f"{name} is empty")
         return float(r[0]), float(r[-1]), capi.RANGE_INT
     a = r[0], r[-1]
-    kinds = set()
+    kinds = []
     for v in a:
         if isinstance(v, (int, np.integer)) and not isinstance(v, (bool, np.bool_)):
-            kinds.add(capi.RANGE_INT)
+            kinds.append(capi.RANGE_INT)
         elif isinstance(v, np.float32):
-            kinds.add(capi.RANGE_F32)
+            kinds.append(capi.RANGE_F32)
         elif isinstance(v, (float, np.float64)):
-            kinds.add(capi.RANGE_F64)
+            kinds.append(capi.RANGE_F64)
         else:
             raise TypeError(f"unsupported endpoint type in {name}: {type(v).__name__}")
-    return float(a[0]), float(a[1]), max(kinds)
+    # The reference takes the vertex type from eltype(first(X)) only (src/marching_cubes.jl:31) but the LinRange
+    # element type from BOTH endpoints (LinRange(first(X), last(X), n), :36-38).  In terms of b200iso_params:
+    #   first is Float64                      -> RANGE_F64 (Float64 coordinates, Float64 vertices)
+    #   else promote(first, last) is Float32  -> RANGE_F32 (Float32 coordinates)
+    #   else                                  -> RANGE_INT (Float64 coordinates, no promotion of the vertex type):
+    #                                            (Int, Int), (Int, Float64), (Float32, Float64)
+    if kinds[0] == capi.RANGE_F64:
+        kind = capi.RANGE_F64
+    elif capi.RANGE_F64 not in kinds and capi.RANGE_F32 in kinds:
+        kind = capi.RANGE_F32
+    else:
+        kind = capi.RANGE_INT
+    return float(a[0]), float(a[1]), kind
 
 
 def make_params(method, X=(-1, 1), Y=(-1, 1), Z=(-1, 1)):
@@ -217,11 +229,13 @@ def _isosurface_torch(t, params, device):
     h = get_handle(dev)
     with torch.cuda.device(dev):
         h.set_stream(torch.cuda.current_stream().cuda_stream)
-        nv, nf, f64 = h.count(params, t.data_ptr(), capi.DEVICE, nx, ny, nz, ldx)
-        verts = torch.empty((nv, 3), dtype=torch.float64 if f64 else torch.float32, device=t.device)
-        faces = torch.empty((nf, 3), dtype=torch.int64, device=t.device)
-        h.generate(verts.data_ptr(), faces.data_ptr(), capi.DEVICE, 0)
-        h.use_own_stream()
+        try:
+            nv, nf, f64 = h.count(params, t.data_ptr(), capi.DEVICE, nx, ny, nz, ldx)
+            verts = torch.empty((nv, 3), dtype=torch.float64 if f64 else torch.float32, device=t.device)
+            faces = torch.empty((nf, 3), dtype=torch.int64, device=t.device)
+            h.generate(verts.data_ptr(), faces.data_ptr(), capi.DEVICE, 0)
+        finally:
+            h.use_own_stream()  # the cached handle must not stay bound to torch's stream if anything raised
     return verts, faces
 
 

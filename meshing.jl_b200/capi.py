@@ -18,6 +18,7 @@ ECAPACITY = -5  # B200ISO_ECAPACITY
 PEER_MAX = 16
 PEER_BYTES = 2 * PEER_MAX * 4 * 8  # B200ISO_PEER_BYTES
 RANGE_INT, RANGE_F32, RANGE_F64 = 0, 1, 2
+CLASSIFY_LDG128, CLASSIFY_TMA, CLASSIFY_SCALAR, CLASSIFY_F64 = 0, 1, 2, 3  # B200ISO_CLASSIFY_*
 
 
 class Params(ctypes.Structure):
@@ -78,7 +79,9 @@ def load():
     L.b200iso_set_peer_exchange.argtypes = [vp, ci, ci, ctypes.POINTER(vp)]
     L.b200iso_exchange_async.argtypes = [vp, vp, vp]
     L.b200iso_add_vertex_base_async.argtypes = [vp, vp, i64, vp, vp]
-    L.b200iso_set_extract_mode.argtypes = [vp, ci]
+    L.b200iso_set_classify_mode.argtypes = [vp, ci]
+    L.b200iso_classify_path.argtypes = [vp]
+    L.b200iso_set_peer_timeout.argtypes = [vp, ctypes.c_double]
     L.b200iso_case_indices.argtypes = [vp, vp, ci]
     L.b200iso_enable_timing.argtypes = [vp, ci]
     L.b200iso_timings.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ci]
@@ -167,9 +170,17 @@ class Handle:
     def exchange_async(self, bases_dev_ptr, all_dev_ptr=0):
         _check(self.L.b200iso_exchange_async(self.h, ctypes.c_void_p(bases_dev_ptr), ctypes.c_void_p(all_dev_ptr or 0)))
 
-    def set_extract_mode(self, mode):
-        """0 = count then generate (default), 1 = fused single-pass kernel"""
-        _check(self.L.b200iso_set_extract_mode(self.h, mode))
+    def set_classify_mode(self, mode):
+        """-1 = automatic (default), 1 = TMA-staged classify whenever the field allows a tensor map, 0 = never TMA"""
+        _check(self.L.b200iso_set_classify_mode(self.h, mode))
+
+    def classify_path(self):
+        """CLASSIFY_* of the last count (-1 before the first)"""
+        return self.L.b200iso_classify_path(self.h)
+
+    def set_peer_timeout(self, seconds):
+        """how long exchange_async waits for its peers; <= 0 waits for ever"""
+        _check(self.L.b200iso_set_peer_timeout(self.h, float(seconds)))
 
     def add_vertex_base_async(self, faces_dev_ptr, fcap, totals_dev_ptr, vertex_base_dev_ptr):
         _check(self.L.b200iso_add_vertex_base_async(self.h, ctypes.c_void_p(faces_dev_ptr), fcap,

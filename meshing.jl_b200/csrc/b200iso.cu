@@ -65,6 +65,21 @@ struct DevBuf {
   }
 };
 
+// Entry points run on the handle's device and put the caller's current device back afterwards (a host process that
+// tracks the current device -- torch, CUDA.jl -- must not find it moved by a library call).
+struct DeviceGuard {
+  int prev = -1, dev;
+  explicit DeviceGuard(int d) : dev(d) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 // smallest float t such that for every float s: (double)s < iso  <=>  s < t   (strict compare,
 // src/common.jl:11-18, after Julia's promotion of both sides to Float64).
 float threshold_for(double iso, bool iso_is_f32) {
@@ -82,11 +97,21 @@ struct b200iso_handle {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   DevBuf<uint32_t> bits;
   DevBuf<uint32_t> celloff;      // MT: per-cell vertex prefix inside its block
-  DevBuf<unsigned long long> status;
-  DevBuf<unsigned long long> woff;  // MC: exclusive (vertex, face) prefix of every generate block; MT (split count): raw block totals
-  DevBuf<unsigned long long> chain2;  // MT (split count): look-back state of the scan blocks
-  long long chain_blocks = 0;       // blocks of the look-back chain of the last count
+  // scan state, cleared by block 0 of the classify kernel: [0] = ticket, [2 ..) = look-back chain of the scan blocks
+  DevBuf<unsigned long long> chain;
+  DevBuf<unsigned long long> status;  // MT: inclusive (vertex, face) prefix of every generate block (FLAG_INC | value)
+  DevBuf<unsigned long long> woff;    // MC: exclusive (vertex, face) prefix of every generate block; MT: raw block totals
   DevBuf<double> coords;
+  DevBuf<uint8_t> cases;             // b200iso_case_indices(HOST): device scratch, kept across calls
+  // grid coordinates are a function of the call's shape and ranges only: recomputed when those change
+  struct CoordsKey {
+    long long nx = -1, ny = -1, nz = -1, xoff = 0, nxg = 0;
+    double r[6] = {0, 0, 0, 0, 0, 0};
+    int f32 = 0;
+    bool operator==(const CoordsKey& o) const {
+      return nx == o.nx && ny == o.ny && nz == o.nz && xoff == o.xoff && nxg == o.nxg && f32 == o.f32 && memcmp(r, o.r, sizeof(r)) == 0;
+    }
+  } coords_key;
   DevBuf<unsigned char> field;   // staging of a host field
   DevBuf<unsigned char> vstage;  // staging of vertices for host output
   DevBuf<long long> fstage;
@@ -94,12 +119,12 @@ struct b200iso_handle {
   DevBuf<long long> fstage1;
   hostpipe::Pool pool;             // copy lanes (streams, pinned chunks, events) of the HOST paths
   std::vector<cudaEvent_t> slab_ev;  // b200iso_extract_host: slab k generated; [n-2] fork, [n-1] join
-  unsigned int* ticket = nullptr;
   long long* totals_dev = nullptr;   // device int64[4]: nverts, nfaces, peer-exchange error flag, spare
   // sharded path: peer exchange of the slab totals (b200iso_set_peer_exchange)
   iso::PeerSlots peers{};
   int peer_rank = 0, peer_world = 0;
   long long peer_epoch = 0;
+  double peer_timeout_s = 60.0;  // b200iso_set_peer_timeout; <= 0 waits for ever (like NCCL)
   long long* totals_host = nullptr;  // pinned int64[2]
   // last counted problem
   bool counted = false, totals_known = false;
@@ -118,9 +143,8 @@ struct b200iso_handle {
   unsigned char* ev_set = nullptr;    // which events of a slot were recorded
   long long step = 0;                 // steps (count calls) since timing was enabled
   int64_t launches = 0;
-  int split_count = 1;  // MC: count chunks, then scan them (1, default) or count with the look-back chain inside (0; env B200ISO_SPLIT_COUNT)
-  int tma_mode = -1;  // classify staging: -1 = TMA boxes on big fields (default), 1 = always TMA, 0 = per-lane 128-bit loads (env B200ISO_TMA)
-  int mode = 0;  // b200iso_extract_async strategy for MC: 0 = count then generate, 1 = fused single pass
+  int tma_mode = -1;  // classify staging: -1 = TMA boxes on big fields (default), 1 = TMA whenever a tensor map exists, 0 = per-lane loads (b200iso_set_classify_mode; env B200ISO_TMA)
+  int classify_path = -1;  // what the last count ran: B200ISO_CLASSIFY_*
   int rec(int which) {
     if (!timing) return 0;
     const int slot = (int)((step > 0 ? step - 1 : 0) % NSLOT);
@@ -160,9 +184,9 @@ int check_params(const b200iso_params* p, int64_t nx, int64_t ny, int64_t nz, in
   return 0;
 }
 
-// fused = true: classify + coordinates only; the caller enqueues the single-pass generate kernel next.
+// classify -> count -> scan (-> grid coordinates when the shape or the ranges changed) on the handle's stream
 int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_dev, int64_t nx, int64_t ny, int64_t nz,
-                  int64_t ldx, long long* totals_out, bool step_begun = false, bool fused = false) {
+                  int64_t ldx, long long* totals_out, bool step_begun = false) {
   cudaStream_t st = h->stream;
   h->prm = *p;
   h->sdf_dev = sdf_dev;
@@ -181,20 +205,25 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
     h->counted = true;
     return 0;
   }
+  const bool mt = p->algo == B200ISO_MT;
   const size_t nbits = (size_t)nx * ny * g.W;
+  const long long per = (long long)iso::SC_THREADS * iso::SC_PER, nsb = (h->nblocks + per - 1) / per;  // scan blocks
   if (int rc = h->bits.reserve(nbits)) return rc;
-  const bool warp_count = p->algo == B200ISO_MC && !fused;
-  h->chain_blocks = warp_count ? (h->nblocks + iso::WC_THREADS / 32 - 1) / (iso::WC_THREADS / 32) : h->nblocks;
-  if (int rc = h->status.reserve((size_t)h->chain_blocks * 2)) return rc;
-  if (warp_count)
-    if (int rc = h->woff.reserve((size_t)h->nblocks * 2)) return rc;
-  if (p->algo == B200ISO_MT)
+  if (int rc = h->chain.reserve((size_t)nsb * 2 + 4)) return rc;
+  if (int rc = h->woff.reserve((size_t)h->nblocks * 2)) return rc;
+  if (mt) {
+    if (int rc = h->status.reserve((size_t)h->nblocks * 2)) return rc;
     if (int rc = h->celloff.reserve(nbits)) return rc;
+  }
   if (int rc = h->coords.reserve((size_t)(nx + ny + nz))) return rc;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(h->chain.p);
+  unsigned long long* chain = h->chain.p + 2;
+  unsigned long long* ghost_words = chain + 2 * nsb;  // MT slabs: inclusive prefix at the end of the ghost row
+  const int nclear = (int)(nsb * 2 + 4);
 
   if (!step_begun) h->begin_step();
   if (int rc = h->rec(b200iso_handle::E_C0)) return rc;
-  // (1) sign-pack
+  // (1) sign-pack; its block 0 also clears the scan state (ticket + chain) -- no memset nodes in the step
   {
     const bool f64 = p->field_is_f64 != 0;
     const bool vec = !f64 && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(sdf_dev) & 15) == 0);
@@ -210,58 +239,53 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
     if (vec && tma_wanted && iso::make_field_tmap(&tmap, sdf_f, nx, ny, nz, ldx)) {
       // TMA-staged classify: same tasks, cp.async.bulk.tensor boxes + per-warp mbarrier pipeline
       const unsigned tb = (unsigned)((ntasks + iso::TM_WARPS - 1) / iso::TM_WARPS);
-      iso::signpack_tma_kernel<<<tb, iso::TM_WARPS * 32, iso::TM_SMEM, st>>>(tmap, h->bits.p, g.nx, g.ny, g.nz, g.W, thr, nxseg, ntasks);
-    } else if (vec)
-      iso::signpack_kernel<true, float><<<nb, iso::SP_WARPS * 32, 0, st>>>(sdf_f, h->bits.p, g.nx, g.ny, g.nz, g.ldx, g.W, thr, nxseg, ntasks);
-    else if (!f64)
-      iso::signpack_kernel<false, float><<<nb, iso::SP_WARPS * 32, 0, st>>>(sdf_f, h->bits.p, g.nx, g.ny, g.nz, g.ldx, g.W, thr, nxseg, ntasks);
-    else  // Float64 field: Float64 < promote(iso) compares exactly in Float64
+      iso::signpack_tma_kernel<<<tb, iso::TM_WARPS * 32, iso::TM_SMEM, st>>>(tmap, h->bits.p, g.nx, g.ny, g.nz, g.W, thr, nxseg, ntasks, h->chain.p, nclear);
+      h->classify_path = B200ISO_CLASSIFY_TMA;
+    } else if (vec) {
+      iso::signpack_kernel<true, float><<<nb, iso::SP_WARPS * 32, 0, st>>>(sdf_f, h->bits.p, g.nx, g.ny, g.nz, g.ldx, g.W, thr, nxseg, ntasks, h->chain.p, nclear);
+      h->classify_path = B200ISO_CLASSIFY_LDG128;
+    } else if (!f64) {
+      iso::signpack_kernel<false, float><<<nb, iso::SP_WARPS * 32, 0, st>>>(sdf_f, h->bits.p, g.nx, g.ny, g.nz, g.ldx, g.W, thr, nxseg, ntasks, h->chain.p, nclear);
+      h->classify_path = B200ISO_CLASSIFY_SCALAR;
+    } else {  // Float64 field: Float64 < promote(iso) compares exactly in Float64
       iso::signpack_kernel<false, double><<<nb, iso::SP_WARPS * 32, 0, st>>>(reinterpret_cast<const double*>(sdf_dev), h->bits.p, g.nx, g.ny,
                                                                            g.nz, g.ldx, g.W, p->iso_is_f32 ? (double)(float)p->iso : p->iso,
-                                                                           nxseg, ntasks);
+                                                                           nxseg, ntasks, h->chain.p, nclear);
+      h->classify_path = B200ISO_CLASSIFY_F64;
+    }
     CU(cudaGetLastError());
     h->launches++;
   }
   if (int rc = h->rec(b200iso_handle::E_C1)) return rc;
-  // (2) count + decoupled look-back scan (in the fused form the generate kernel does this itself)
-  CU(cudaMemsetAsync(h->status.p, 0, (size_t)h->chain_blocks * 2 * sizeof(unsigned long long), st));
-  CU(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned int), st));
+  // (2) count (raw totals per generate block), then a light single-pass decoupled look-back scan over them
   h->totals_out = totals_out;
-  if (fused) {
-  } else if (p->algo == B200ISO_MC && h->split_count) {
-    // (a) raw per-chunk counts, (b) light single-pass look-back scan over them (count_kernel.cuh)
-    iso::mc_count_chunks_kernel<<<(unsigned)h->chain_blocks, iso::WC_THREADS, 0, st>>>(h->bits.p, g, h->nblocks, h->woff.p);
+  if (!mt) {
+    const unsigned ncb = (unsigned)((h->nblocks + iso::WC_THREADS / 32 - 1) / (iso::WC_THREADS / 32));
+    iso::mc_count_chunks_kernel<<<ncb, iso::WC_THREADS, 0, st>>>(h->bits.p, g, h->nblocks, h->woff.p);
     CU(cudaGetLastError());
-    h->launches++;
-    const long long per = (long long)iso::SC_THREADS * iso::SC_PER, nsb = (h->nblocks + per - 1) / per;
-    iso::mc_scan_chunks_kernel<<<(unsigned)nsb, iso::SC_THREADS, 0, st>>>(h->woff.p, h->nblocks, h->status.p, h->ticket, nsb, h->totals_dev, totals_out);
-  } else if (p->algo == B200ISO_MC)
-    iso::mc_count_warp_kernel<<<(unsigned)h->chain_blocks, iso::WC_THREADS, 0, st>>>(h->bits.p, g, h->nblocks, h->status.p, h->ticket,
-                                                                                   h->chain_blocks, h->totals_dev, totals_out, h->woff.p);
-  else if (h->split_count) {
-    // MT, split form: raw block totals -> light look-back scan into the inclusive prefixes generate reads
-    const long long per = (long long)iso::SC_THREADS * iso::SC_PER, nsb = (h->nblocks + per - 1) / per;
-    if (int rc = h->woff.reserve((size_t)h->nblocks * 2)) return rc;
-    if (int rc = h->chain2.reserve((size_t)nsb * 2)) return rc;
-    CU(cudaMemsetAsync(h->chain2.p, 0, (size_t)nsb * 2 * sizeof(unsigned long long), st));
-    iso::count_kernel<1><<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->status.p, h->ticket, h->nblocks, h->totals_dev, totals_out,
-                                                                           h->celloff.p, h->woff.p);
+    iso::mc_scan_chunks_kernel<<<(unsigned)nsb, iso::SC_THREADS, 0, st>>>(h->woff.p, h->nblocks, chain, ticket, nsb, h->totals_dev, totals_out);
+  } else {
+    iso::mt_count_kernel<<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->celloff.p, h->woff.p);
     CU(cudaGetLastError());
-    h->launches++;
-    iso::mt_scan_blocks_kernel<<<(unsigned)nsb, iso::SC_THREADS, 0, st>>>(h->woff.p, h->nblocks, h->status.p, h->chain2.p, h->ticket, nsb,
-                                                                          g.ghost ? (long long)g.blocks_per_row - 1 : -1LL, h->totals_dev, totals_out);
-  } else
-    iso::count_kernel<1><<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->status.p, h->ticket, h->nblocks, h->totals_dev, totals_out, h->celloff.p);
+    iso::mt_scan_blocks_kernel<<<(unsigned)nsb, iso::SC_THREADS, 0, st>>>(h->woff.p, h->nblocks, h->status.p, chain, ticket, nsb,
+                                                                          g.ghost ? (long long)g.blocks_per_row - 1 : -1LL, ghost_words, h->totals_dev, totals_out);
+  }
   CU(cudaGetLastError());
-  h->launches++;
-  // grid coordinates (LinRange), consumed by generate
+  h->launches += 2;
+  // grid coordinates (LinRange), consumed by generate: a function of the shape and the ranges only
   {
-    const int n = (int)(nx + ny + nz);
-    iso::coords_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->coords.p, g.nx, g.ny, g.nz, p->x0, p->x1, p->y0, p->y1, p->z0, p->z1,
-                                                        p->range_kind == B200ISO_RANGE_F32, (int)p->x_offset,
-                                                        (int)(p->nx_global > 0 ? p->nx_global : nx));
-    CU(cudaGetLastError());
-    h->launches++;
+    b200iso_handle::CoordsKey key;
+    key.nx = nx, key.ny = ny, key.nz = nz, key.xoff = p->x_offset, key.nxg = p->nx_global > 0 ? p->nx_global : nx;
+    key.r[0] = p->x0, key.r[1] = p->x1, key.r[2] = p->y0, key.r[3] = p->y1, key.r[4] = p->z0, key.r[5] = p->z1;
+    key.f32 = p->range_kind == B200ISO_RANGE_F32;
+    if (!(key == h->coords_key)) {
+      const int n = (int)(nx + ny + nz);
+      iso::coords_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->coords.p, g.nx, g.ny, g.nz, p->x0, p->x1, p->y0, p->y1, p->z0, p->z1, key.f32,
+                                                          (int)key.xoff, (int)key.nxg);
+      CU(cudaGetLastError());
+      h->launches++;
+      h->coords_key = key;
+    }
   }
   if (int rc = h->rec(b200iso_handle::E_C2)) return rc;
   h->counted = true;
@@ -269,7 +293,7 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
 }
 
 int enqueue_generate(b200iso_handle* h, void* verts_dev, int64_t vcap, int64_t* faces_dev, int64_t fcap,
-                     const int64_t* vertex_base_dev, int64_t vertex_base, bool fused = false) {
+                     const int64_t* vertex_base_dev, int64_t vertex_base) {
   if (!h->counted) return fail(B200ISO_ESTATE, "generate called before count");
   cudaStream_t st = h->stream;
   if (int rc = h->rec(b200iso_handle::E_G0)) return rc;
@@ -282,21 +306,15 @@ int enqueue_generate(b200iso_handle* h, void* verts_dev, int64_t vcap, int64_t* 
     a.iso_d = p.iso, a.iso_f = (float)p.iso, a.eps_d = p.eps, a.eps_f = (float)p.eps;
     a.iso_is_f32 = p.iso_is_f32, a.eps_is_f32 = p.eps_is_f32, a.p_is_f32 = p.range_kind == B200ISO_RANGE_F32;
     a.sdf_vec = !p.field_is_f64 && h->grid.ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(h->sdf_dev) & 15) == 0;
-    a.ticket = h->ticket, a.nblocks = h->nblocks, a.totals_a = h->totals_dev, a.totals_b = h->totals_out;
+    a.nblocks = h->nblocks, a.totals_a = h->totals_dev, a.abort_flag = h->totals_dev + 2;
     const unsigned nb = (unsigned)h->nblocks;
     const bool pf32 = p.range_kind == B200ISO_RANGE_F32;
-    if (p.algo == B200ISO_MC && fused) {
-      if (p.field_is_f64) iso::mc_generate_kernel<3, double, true><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
-      else if (!p.iso_is_f32) iso::mc_generate_kernel<2, double, true><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
-      else if (pf32) iso::mc_generate_kernel<1, float, true><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
-      else if (h->vert_is_f64) iso::mc_generate_kernel<0, double, true><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
-      else iso::mc_generate_kernel<0, float, true><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
-    } else if (p.algo == B200ISO_MC) {
-      if (p.field_is_f64) iso::mc_generate_kernel<3, double, false><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
-      else if (!p.iso_is_f32) iso::mc_generate_kernel<2, double, false><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
-      else if (pf32) iso::mc_generate_kernel<1, float, false><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
-      else if (h->vert_is_f64) iso::mc_generate_kernel<0, double, false><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
-      else iso::mc_generate_kernel<0, float, false><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+    if (p.algo == B200ISO_MC) {
+      if (p.field_is_f64) iso::mc_generate_kernel<3, double><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+      else if (!p.iso_is_f32) iso::mc_generate_kernel<2, double><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+      else if (pf32) iso::mc_generate_kernel<1, float><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+      else if (h->vert_is_f64) iso::mc_generate_kernel<0, double><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
+      else iso::mc_generate_kernel<0, float><<<nb, iso::CB_THREADS, 0, st>>>(a, h->grid);
     } else {
       if (int rc = iso::launch_mt_generate(a, h->grid, p, h->vert_is_f64, h->celloff.p, nb, st)) return fail(B200ISO_EINVAL, "MT launch failed (%d)", rc);
     }
@@ -314,7 +332,7 @@ int fetch_totals(b200iso_handle* h) {
     CU(cudaStreamSynchronize(h->stream));
     if (h->totals_host[2] != 0) {
       cudaMemsetAsync(h->totals_dev + 2, 0, sizeof(long long), h->stream);
-      return fail(B200ISO_ESTATE, "peer exchange timed out: a rank did not publish its totals");
+      return fail(B200ISO_ESTATE, "peer exchange timed out: a rank did not publish its totals (re-arm with b200iso_set_peer_exchange on zeroed buffers)");
     }
     h->nverts = h->totals_host[0], h->nfaces = h->totals_host[1];
     h->totals_known = true;
@@ -326,8 +344,20 @@ int fetch_totals(b200iso_handle* h) {
 
 extern "C" {
 
-int b200iso_version(void) { return 1000; }
+int b200iso_version(void) { return 2000; }
 const char* b200iso_last_error(void) { return g_err; }
+
+static int create_impl(b200iso_handle* h) {
+  if (const char* e = getenv("B200ISO_TMA")) h->tma_mode = atoi(e) != 0 ? 1 : 0;
+  // per device: the TMA classify kernel needs more than the default 48 KB of dynamic shared memory
+  CU(cudaFuncSetAttribute(iso::signpack_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iso::TM_SMEM));
+  CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  CU(cudaMalloc((void**)&h->totals_dev, 4 * sizeof(long long)));
+  CU(cudaMemset(h->totals_dev, 0, 4 * sizeof(long long)));
+  CU(cudaMallocHost((void**)&h->totals_host, 4 * sizeof(long long)));
+  return 0;
+}
 
 int b200iso_create(b200iso_handle** out, int device) {
   if (!out) return fail(B200ISO_EINVAL, "out is NULL");
@@ -335,33 +365,28 @@ int b200iso_create(b200iso_handle** out, int device) {
   int ndev = 0;
   CU(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(B200ISO_EINVAL, "device %d out of range (%d devices)", device, ndev);
-  CU(cudaSetDevice(device));
-  b200iso_handle* h = new b200iso_handle();
+  DeviceGuard guard(device);
+  b200iso_handle* h = new (std::nothrow) b200iso_handle();
+  if (!h) return fail(B200ISO_ENOMEM, "out of host memory");
   h->device = device;
   h->pool.device = device;
-  if (const char* e = getenv("B200ISO_TMA")) h->tma_mode = atoi(e) != 0 ? 1 : 0;
-  if (const char* e = getenv("B200ISO_SPLIT_COUNT")) h->split_count = atoi(e) != 0 ? 1 : 0;
-  // per device: the TMA classify kernel needs more than the default 48 KB of dynamic shared memory
-  CU(cudaFuncSetAttribute(iso::signpack_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iso::TM_SMEM));
-  CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-  h->stream = h->own_stream;
-  CU(cudaMalloc((void**)&h->ticket, sizeof(unsigned int)));
-  CU(cudaMalloc((void**)&h->totals_dev, 4 * sizeof(long long)));
-  CU(cudaMemset(h->totals_dev, 0, 4 * sizeof(long long)));
-  CU(cudaMallocHost((void**)&h->totals_host, 4 * sizeof(long long)));
+  if (int rc = create_impl(h)) {  // (the message of the failing call stays in g_err)
+    b200iso_destroy(h);
+    return rc;
+  }
   *out = h;
   return 0;
 }
 
 int b200iso_destroy(b200iso_handle* h) {
   if (!h) return 0;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   cudaDeviceSynchronize();  // (the caller's stream may already be gone: do not touch h->stream)
   h->vstage1.release(), h->fstage1.release();
   for (cudaEvent_t e : h->slab_ev) cudaEventDestroy(e);
   h->pool.release();
-  h->bits.release(), h->celloff.release(), h->woff.release(), h->chain2.release(), h->status.release(), h->coords.release(), h->field.release(), h->vstage.release(), h->fstage.release();
-  if (h->ticket) cudaFree(h->ticket);
+  h->bits.release(), h->celloff.release(), h->woff.release(), h->chain.release(), h->status.release(), h->coords.release(), h->field.release(), h->vstage.release(), h->fstage.release();
+  h->cases.release();
   if (h->totals_dev) cudaFree(h->totals_dev);
   if (h->totals_host) cudaFreeHost(h->totals_host);
   if (h->ev) {
@@ -370,6 +395,7 @@ int b200iso_destroy(b200iso_handle* h) {
     delete[] h->ev_set;
   }
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  cudaGetLastError();
   delete h;
   return 0;
 }
@@ -377,12 +403,28 @@ int b200iso_destroy(b200iso_handle* h) {
 int b200iso_set_stream(b200iso_handle* h, void* cuda_stream) {
   if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
   h->stream = (cudaStream_t)cuda_stream;
+  h->coords_key = b200iso_handle::CoordsKey();  // the cached grid coordinates were produced on the previous stream
   return 0;
 }
 
 int b200iso_use_own_stream(b200iso_handle* h) {
   if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
   h->stream = h->own_stream;
+  h->coords_key = b200iso_handle::CoordsKey();
+  return 0;
+}
+
+int b200iso_set_classify_mode(b200iso_handle* h, int mode) {
+  if (!h || mode < -1 || mode > 1) return fail(B200ISO_EINVAL, "bad handle or classify mode");
+  h->tma_mode = mode;
+  return 0;
+}
+
+int b200iso_classify_path(b200iso_handle* h) { return h ? h->classify_path : -1; }
+
+int b200iso_set_peer_timeout(b200iso_handle* h, double seconds) {
+  if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  h->peer_timeout_s = seconds;
   return 0;
 }
 
@@ -391,7 +433,7 @@ int b200iso_count_async(b200iso_handle* h, const b200iso_params* p, const void* 
   if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
   if (int rc = check_params(p, nx, ny, nz, ldx)) return rc;
   if (!sdf_dev && nx * ny * nz > 0) return fail(B200ISO_EINVAL, "sdf is NULL");
-  CU(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   return enqueue_count(h, p, sdf_dev, nx, ny, nz, ldx, (long long*)totals_dev);
 }
 
@@ -400,7 +442,7 @@ int b200iso_generate_async(b200iso_handle* h, void* verts_dev, int64_t vcap, int
   if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
   if (vcap < 0 || fcap < 0) return fail(B200ISO_EINVAL, "negative capacity");
   if ((vcap > 0 && !verts_dev) || (fcap > 0 && !faces_dev)) return fail(B200ISO_EINVAL, "output pointer is NULL");
-  CU(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   return enqueue_generate(h, verts_dev, vcap, faces_dev, fcap, vertex_base_dev, vertex_base);
 }
 
@@ -412,10 +454,9 @@ int b200iso_extract_async(b200iso_handle* h, const b200iso_params* p, const void
   if (!sdf_dev && nx * ny * nz > 0) return fail(B200ISO_EINVAL, "sdf is NULL");
   if (vcap < 0 || fcap < 0) return fail(B200ISO_EINVAL, "negative capacity");
   if ((vcap > 0 && !verts_dev) || (fcap > 0 && !faces_dev)) return fail(B200ISO_EINVAL, "output pointer is NULL");
-  CU(cudaSetDevice(h->device));
-  const bool fused = p->algo == B200ISO_MC && h->mode == 1;
-  if (int rc = enqueue_count(h, p, sdf_dev, nx, ny, nz, ldx, (long long*)totals_dev, false, fused)) return rc;
-  return enqueue_generate(h, verts_dev, vcap, faces_dev, fcap, vertex_base_dev, vertex_base, fused);
+  DeviceGuard guard(h->device);
+  if (int rc = enqueue_count(h, p, sdf_dev, nx, ny, nz, ldx, (long long*)totals_dev)) return rc;
+  return enqueue_generate(h, verts_dev, vcap, faces_dev, fcap, vertex_base_dev, vertex_base);
 }
 
 int b200iso_add_vertex_base_async(b200iso_handle* h, int64_t* faces_dev, int64_t fcap, const int64_t* totals_dev,
@@ -423,7 +464,7 @@ int b200iso_add_vertex_base_async(b200iso_handle* h, int64_t* faces_dev, int64_t
   if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
   if (!faces_dev || !totals_dev || !vertex_base_dev) return fail(B200ISO_EINVAL, "NULL argument");
   if ((reinterpret_cast<uintptr_t>(faces_dev) & 15) != 0) return fail(B200ISO_EINVAL, "faces must be 16-byte aligned");
-  CU(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   iso::add_base_kernel<<<148 * 8, 256, 0, h->stream>>>((long long*)faces_dev, fcap, (const long long*)totals_dev,
                                                        (const long long*)vertex_base_dev);
   CU(cudaGetLastError());
@@ -443,6 +484,8 @@ int b200iso_set_peer_exchange(b200iso_handle* h, int rank, int world, void* cons
     h->peers.slot[r] = (long long*)slots[r];
   }
   h->peer_rank = rank, h->peer_world = world, h->peer_epoch = 0;
+  DeviceGuard guard(h->device);
+  CU(cudaMemsetAsync(h->totals_dev + 2, 0, sizeof(long long), h->stream));  // re-armed: a previous time-out is forgotten
   return 0;
 }
 
@@ -451,21 +494,20 @@ int b200iso_exchange_async(b200iso_handle* h, int64_t* bases_dev, int64_t* all_d
   if (!h->counted) return fail(B200ISO_ESTATE, "exchange called before count");
   if (h->peer_world <= 1) return fail(B200ISO_ESTATE, "no peer exchange configured (b200iso_set_peer_exchange)");
   if (!bases_dev) return fail(B200ISO_EINVAL, "bases_dev is NULL");
-  CU(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   const long long epoch = ++h->peer_epoch;
-  iso::peer_publish_kernel<<<1, 32, 0, h->stream>>>(h->peers, h->peer_world, h->peer_rank, epoch, h->totals_dev);
+  const unsigned long long timeout_ns = h->peer_timeout_s > 0 ? (unsigned long long)(h->peer_timeout_s * 1e9) : 0ull;
+  iso::peer_exchange_kernel<<<1, 32, 0, h->stream>>>(h->peers, h->peer_world, h->peer_rank, epoch, h->totals_dev, (long long*)bases_dev,
+                                                     (long long*)all_dev, h->totals_dev + 2, timeout_ns);
   CU(cudaGetLastError());
-  iso::peer_gather_kernel<<<1, 32, 0, h->stream>>>(h->peers.slot[h->peer_rank], h->peer_world, h->peer_rank, epoch, (long long*)bases_dev,
-                                                   (long long*)all_dev, h->totals_dev + 2);
-  CU(cudaGetLastError());
-  h->launches += 2;
+  h->launches += 1;
   h->totals_known = false;  // the next b200iso_totals re-reads the totals together with the exchange's error flag
   return 0;
 }
 
 int b200iso_totals(b200iso_handle* h, int64_t* nverts, int64_t* nfaces, int* vert_is_f64) {
   if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
-  CU(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   if (int rc = fetch_totals(h)) return rc;
   if (nverts) *nverts = h->nverts;
   if (nfaces) *nfaces = h->nfaces;
@@ -479,7 +521,7 @@ static int b200iso_count_impl(b200iso_handle* h, const b200iso_params* p, const 
   if (int rc = check_params(p, nx, ny, nz, ldx)) return rc;
   if (mem != B200ISO_HOST && mem != B200ISO_DEVICE) return fail(B200ISO_EINVAL, "bad mem kind %d", mem);
   if (!sdf && nx * ny * nz > 0) return fail(B200ISO_EINVAL, "sdf is NULL");
-  CU(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   const void* dev = sdf;
   int64_t dldx = ldx;
   const size_t esz = p->field_is_f64 ? 8 : 4;
@@ -533,7 +575,7 @@ int b200iso_count(b200iso_handle* h, const b200iso_params* p, const void* sdf, i
 static int b200iso_generate_impl(b200iso_handle* h, void* verts, int64_t* faces, int mem, int64_t vertex_base) {
   if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
   if (mem != B200ISO_HOST && mem != B200ISO_DEVICE) return fail(B200ISO_EINVAL, "bad mem kind %d", mem);
-  CU(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   if (int rc = fetch_totals(h)) return rc;
   const size_t vsz = h->vert_is_f64 ? 8 : 4;
   if ((h->nverts > 0 && !verts) || (h->nfaces > 0 && !faces)) return fail(B200ISO_EINVAL, "output pointer is NULL");
@@ -597,7 +639,7 @@ static int b200iso_extract_host_impl(b200iso_handle* h, const b200iso_params* p,
   if (!sdf && nx * ny * nz > 0) return fail(B200ISO_EINVAL, "sdf is NULL");
   if (vcap < 0 || fcap < 0) return fail(B200ISO_EINVAL, "negative capacity");
   if ((vcap > 0 && !verts) || (fcap > 0 && !faces)) return fail(B200ISO_EINVAL, "output pointer is NULL");
-  CU(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   const int f64 = vertex_is_f64(*p);
   if (vert_is_f64) *vert_is_f64 = f64;
   if (nverts) *nverts = 0;
@@ -710,16 +752,15 @@ int b200iso_extract_host(b200iso_handle* h, const b200iso_params* p, const void*
 int b200iso_case_indices(b200iso_handle* h, uint8_t* out, int mem) {
   if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
   if (!h->counted) return fail(B200ISO_ESTATE, "no counted field");
-  CU(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   const iso::Grid& g = h->grid;
   if (h->nblocks == 0) return 0;
   const long long nvox = (long long)(g.nx - 1) * (g.ny - 1) * (g.nz - 1);
   if (!out) return fail(B200ISO_EINVAL, "out is NULL");
   uint8_t* dev = out;
-  DevBuf<uint8_t> tmp;
   if (mem == B200ISO_HOST) {
-    if (int rc = tmp.reserve((size_t)nvox)) return rc;
-    dev = tmp.p;
+    if (int rc = h->cases.reserve((size_t)nvox)) return rc;
+    dev = h->cases.p;
   }
   const unsigned nb = (unsigned)((nvox + 255) / 256);
   if (h->prm.algo == B200ISO_MC) iso::case_kernel<0><<<nb, 256, 0, h->stream>>>(h->bits.p, g, dev, nvox);
@@ -728,14 +769,13 @@ int b200iso_case_indices(b200iso_handle* h, uint8_t* out, int mem) {
   h->launches++;
   if (e == cudaSuccess && mem == B200ISO_HOST) e = cudaMemcpyAsync(out, dev, (size_t)nvox, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  tmp.release();
   if (e != cudaSuccess) return fail(B200ISO_ECUDA, "case_indices: %s", cudaGetErrorString(e));
   return 0;
 }
 
 int b200iso_enable_timing(b200iso_handle* h, int on) {
   if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
-  CU(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   if (on && !h->ev) {
     const int n = b200iso_handle::NSLOT * b200iso_handle::E_N;
     h->ev = new cudaEvent_t[n];
@@ -753,7 +793,7 @@ int b200iso_timings(b200iso_handle* h, float* ms, int n) {
   double sum[5] = {0, 0, 0, 0, 0};
   long long cnt[5] = {0, 0, 0, 0, 0};
   if (h->ev && h->step > 0) {
-    CU(cudaSetDevice(h->device));
+    DeviceGuard guard(h->device);
     CU(cudaStreamSynchronize(h->stream));
     const long long nsteps = h->step < H::NSLOT ? h->step : H::NSLOT;
     static const int span[5][2] = {{H::E_C0, H::E_C1}, {H::E_C1, H::E_C2}, {H::E_G0, H::E_G1}, {H::E_H0, H::E_H1}, {H::E_D0, H::E_D1}};
@@ -771,11 +811,5 @@ int b200iso_timings(b200iso_handle* h, float* ms, int n) {
 }
 
 int64_t b200iso_launch_count(b200iso_handle* h) { return h ? h->launches : 0; }
-
-int b200iso_set_extract_mode(b200iso_handle* h, int mode) {
-  if (!h || mode < 0 || mode > 1) return fail(B200ISO_EINVAL, "bad handle or mode");
-  h->mode = mode;
-  return 0;
-}
 
 }  // extern "C"

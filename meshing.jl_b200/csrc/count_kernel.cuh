@@ -1,11 +1,12 @@
-// count_kernel.cuh -- (2) count + single-pass decoupled look-back scan.  ALGO 0 = MC, 1 = MT.
+// count_kernel.cuh -- (2) count + single-pass decoupled look-back scan.
 //
-// Used by the two-phase ABI (b200iso_count -> caller allocates -> b200iso_generate) and by MT; the
-// single-GPU MC fast path fuses this work into mc_generate_kernel<.., FUSED = true>.
-// Same block/thread mapping as generate (thread_map): one thread per quad-cell, thread order == scan order.
-// Blocks are numbered through an atomic ticket and publish their totals to the look-back chain.
-//   MC: vertices = crossed cube edges (12 masked popcounts per word), faces = table per active voxel
-//   MT: vertices = owned crossed edges (7+ masked popcounts per word), faces = table per active voxel;
+// Counting and scanning are separate kernels (a look-back chain over the counting blocks themselves makes every
+// block wait for the slowest one ahead of it: measured 0.233 -> 0.180 ms on the gyroid, 0.355 -> 0.189 ms on the
+// clustered multi-sphere/torus field):
+//   MC: mc_count_chunks_kernel (a warp per generate block: raw (vertex, face) pair)  -> mc_scan_chunks_kernel
+//       vertices = crossed cube edges (12 masked popcounts per word), faces = table per active voxel
+//   MT: mt_count_kernel (block-cooperative, same thread mapping as generate)         -> mt_scan_blocks_kernel
+//       vertices = owned crossed edges (7+ masked popcounts per word), faces = table per active voxel;
 //       additionally writes celloff[cell] = vertices created in this block before the cell, which the
 //       generate kernel uses to resolve vertex ids through owner voxels of other blocks.
 #pragma once
@@ -14,21 +15,14 @@
 
 namespace iso {
 
-template <int ALGO>
 __global__ void __launch_bounds__(CB_THREADS)
-count_kernel(const uint32_t* __restrict__ bits, Grid g, unsigned long long* status, unsigned int* ticket,
-             long long nblocks, long long* totals_a, long long* totals_b, uint32_t* __restrict__ celloff,
-             unsigned long long* __restrict__ raw = nullptr) {
+mt_count_kernel(const uint32_t* __restrict__ bits, Grid g, uint32_t* __restrict__ celloff, unsigned long long* __restrict__ raw) {
   __shared__ uint8_t nf_s[256];
   __shared__ uint32_t s_w[CB_THREADS / 32];
   __shared__ uint32_t red_v[CB_THREADS / 32], red_f[CB_THREADS / 32];
-  __shared__ unsigned sb;
-  // raw != nullptr: split form -- store the block's (vertex, face) totals, mt_scan_blocks_kernel scans them afterwards
-  // (no chain over the counting blocks: see the note at mc_count_chunks_kernel)
-  if (threadIdx.x == 0) sb = raw ? blockIdx.x : atomicAdd(ticket, 1u);
-  for (int i = threadIdx.x; i < 256; i += CB_THREADS) nf_s[i] = ALGO == 0 ? (uint8_t)((ISO_MC_VERTS[i] >> 52) & 7) : ISO_MT_NF[i];
+  for (int i = threadIdx.x; i < 256; i += CB_THREADS) nf_s[i] = ISO_MT_NF[i];
   __syncthreads();
-  const unsigned b = sb;
+  const unsigned b = blockIdx.x;
   const TMap tm = thread_map(g, b);
   uint32_t nv = 0, nf = 0;
   uint32_t cv[4] = {0, 0, 0, 0};
@@ -40,18 +34,18 @@ count_kernel(const uint32_t* __restrict__ bits, Grid g, unsigned long long* stat
       for (int i = 0; i < 4; ++i) {
         uint32_t mm = active_mask(q, i);
         if (mm) {
-          cv[i] = ALGO == 0 ? mc_nverts_masked(q, i, q.vm[i]) : mt_owned_masked(q, i, q.vm[i], fxy, tm.zq == 0 && i == 0);
+          cv[i] = mt_owned_masked(q, i, q.vm[i], fxy, tm.zq == 0 && i == 0);
           nv += cv[i];
           while (mm) {
             const int k = __ffs(mm) - 1;
             mm &= mm - 1;
-            nf += nf_s[case_of<ALGO>(q, i, k)];
+            nf += nf_s[case_of<1>(q, i, k)];
           }
         }
       }
     }
   }
-  if (ALGO == 1) {
+  {
     // in-block exclusive vertex prefix of every cell (thread order == scan order)
     uint32_t tot;
     const uint32_t e0 = block_excl_scan_u32(nv, s_w, tot);
@@ -61,7 +55,7 @@ count_kernel(const uint32_t* __restrict__ bits, Grid g, unsigned long long* stat
       *reinterpret_cast<uint4*>(celloff + (long long)tm.x * g.row_words + (long long)tm.y * g.W + tm.zq * 4) = o;
     }
   }
-  // block totals
+  // block totals -> raw[b]; mt_scan_blocks_kernel scans them afterwards
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     nv += __shfl_xor_sync(0xffffffffu, nv, o);
@@ -69,42 +63,18 @@ count_kernel(const uint32_t* __restrict__ bits, Grid g, unsigned long long* stat
   }
   if ((threadIdx.x & 31) == 0) red_v[threadIdx.x >> 5] = nv, red_f[threadIdx.x >> 5] = nf;
   __syncthreads();
-  if (threadIdx.x < 32) {
+  if (threadIdx.x == 0) {
     unsigned long long av = 0, af = 0;
 #pragma unroll
     for (int w = 0; w < CB_THREADS / 32; ++w) av += red_v[w], af += red_f[w];
-    if (raw) {
-      if (threadIdx.x == 0) raw[2 * (unsigned long long)b] = av, raw[2 * (unsigned long long)b + 1] = af;
-      return;
-    }
-    unsigned long long ev, ef;
-    lookback(status, (long long)b, av, af, ev, ef);
-    if ((long long)b == nblocks - 1 && threadIdx.x == 0) {
-      // a ghost row (MT sharding) is counted for the owner look-ups but belongs to the previous slab
-      unsigned long long gv = 0, gf = 0;
-      if (g.ghost) {
-        const long long gb = g.blocks_per_row - 1;  // last block of voxel row 0
-        if (gb == (long long)b) {
-          gv = ev + av, gf = ef + af;
-        } else {
-          unsigned long long sv, sf;
-          do {  // that block publishes its inclusive prefix as soon as its own look-back is done
-            sv = ld_relaxed(status + 2 * gb), sf = ld_relaxed(status + 2 * gb + 1);
-          } while ((sv >> 62) != 2 || (sf >> 62) != 2);
-          gv = sv & VAL_MASK, gf = sf & VAL_MASK;
-        }
-      }
-      totals_a[0] = (long long)(ev + av - gv), totals_a[1] = (long long)(ef + af - gf);
-      if (totals_b) totals_b[0] = totals_a[0], totals_b[1] = totals_a[1];
-    }
+    raw[2 * (unsigned long long)b] = av, raw[2 * (unsigned long long)b + 1] = af;
   }
 }
 
 // ------------------------------------------------------------------------------------------------------
 // Marching Cubes count, warp-autonomous: a warp walks one generate block's quad-cells (lane <-> quad-cell,
-// 32 at a time), only the per-block publication to the look-back chain needs a barrier; the exclusive
-// (vertex, face) prefix of EVERY generate block is written to `woff`.
-constexpr int WC_THREADS = 256;  // 8 warps = 8 generate blocks per chain block
+// 32 at a time) and stores the block's raw (vertex, face) pair -- no chain, no ticket, no barrier.
+constexpr int WC_THREADS = 256;  // 8 warps = 8 generate blocks per counting block
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
   const int lane = threadIdx.x & 31;
@@ -116,78 +86,6 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
   return v;
 }
 
-__global__ void __launch_bounds__(WC_THREADS)
-mc_count_warp_kernel(const uint32_t* __restrict__ bits, Grid g, long long nchunks, unsigned long long* status, unsigned int* ticket,
-                     long long nblocks, long long* totals_a, long long* totals_b, unsigned long long* __restrict__ woff) {
-  __shared__ uint8_t nf_s[256];
-  __shared__ uint32_t wv_s[WC_THREADS / 32], wf_s[WC_THREADS / 32];
-  __shared__ unsigned sb;
-  if (threadIdx.x == 0) sb = atomicAdd(ticket, 1u);
-  nf_s[threadIdx.x] = (uint8_t)((ISO_MC_VERTS[threadIdx.x] >> 52) & 7);
-  __syncthreads();
-  const unsigned b = sb;
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long chunk = (long long)b * (WC_THREADS / 32) + w;
-  uint32_t nv = 0, nf = 0;
-  if (chunk < nchunks) {
-    // chunk == generate block: CB_THREADS consecutive quad-cells of one voxel x-row, walked 32 at a time
-    const int x = (int)(chunk / g.blocks_per_row);
-    const int q_lo = (int)(chunk - (long long)x * g.blocks_per_row) * CB_THREADS;
-    for (int q0 = q_lo; q0 < q_lo + CB_THREADS && q0 < g.quads_per_row; q0 += 32) {
-      TMap tm;
-      const int qr = q0 + lane;
-      tm.x = x, tm.y = (int)fast_div((unsigned)qr, g.wq_mul, g.wq_sh), tm.zq = qr - tm.y * g.Wq, tm.live = qr < g.quads_per_row;
-      Quad q;
-      if (tm.live && load_quad(bits, g, tm.x, tm.y, tm.zq, q)) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint32_t mm = active_mask(q, i);
-          if (mm) {
-            nv += mc_nverts_masked(q, i, q.vm[i]);
-            while (mm) {
-              const int k = __ffs(mm) - 1;
-              mm &= mm - 1;
-              nf += nf_s[case_of<0>(q, i, k)];
-            }
-          }
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    nv += __shfl_xor_sync(0xffffffffu, nv, o);
-    nf += __shfl_xor_sync(0xffffffffu, nf, o);
-  }
-  if (lane == 0) wv_s[w] = nv, wf_s[w] = nf;
-  __syncthreads();
-  if (w == 0) {
-    // per-warp exclusive prefixes inside the block, block aggregate, look-back, publish
-    const uint32_t mv = lane < WC_THREADS / 32 ? wv_s[lane] : 0u, mf = lane < WC_THREADS / 32 ? wf_s[lane] : 0u;
-    const uint32_t iv = warp_incl_scan(mv), jf = warp_incl_scan(mf);
-    const unsigned long long av = __shfl_sync(0xffffffffu, iv, 31), af = __shfl_sync(0xffffffffu, jf, 31);
-    unsigned long long ev, ef;
-    lookback(status, (long long)b, av, af, ev, ef);
-    const long long cc = (long long)b * (WC_THREADS / 32) + lane;
-    if (lane < WC_THREADS / 32 && cc < nchunks) {
-      woff[2 * cc] = ev + (iv - mv);
-      woff[2 * cc + 1] = ef + (jf - mf);
-    }
-    if ((long long)b == nblocks - 1 && lane == 0) {
-      totals_a[0] = (long long)(ev + av), totals_a[1] = (long long)(ef + af);
-      if (totals_b) totals_b[0] = (long long)(ev + av), totals_b[1] = (long long)(ef + af);
-    }
-  }
-}
-
-
-// ---- split form: counting and scanning in two kernels -----------------------------------------------------
-// In mc_count_warp_kernel the look-back chain runs over the counting blocks themselves: a block that sits on a dense
-// piece of surface counts for much longer than its neighbours, and every block behind it in the chain finishes its
-// own work and then waits for that one aggregate.  On fields with clustered surfaces (multi-sphere/torus: 0.35 ms)
-// that costs more than the counting.  Split: (a) every warp counts its chunk and stores the raw pair -- no chain, no
-// ticket, no barrier; (b) a single-pass decoupled look-back scan over the stored pairs, whose blocks are uniform
-// and tiny (1024 pairs each), turns them into exclusive prefixes in place.
 // (launch bound 6 blocks/SM = 40 registers, 75 % occupancy: 0.171 ms against 0.174 at 5 and 0.179 at 4 blocks/SM)
 __global__ void __launch_bounds__(WC_THREADS, 6)
 mc_count_chunks_kernel(const uint32_t* __restrict__ bits, Grid g, long long nchunks, unsigned long long* __restrict__ woff) {
@@ -288,8 +186,8 @@ mc_scan_chunks_kernel(unsigned long long* __restrict__ woff, long long nchunks, 
 // block writes the totals, minus the ghost row of an MT slab (its prefix ends at block blocks_per_row - 1).
 __global__ void __launch_bounds__(SC_THREADS)
 mt_scan_blocks_kernel(const unsigned long long* __restrict__ raw, long long nblocks, unsigned long long* status,
-                      unsigned long long* chain, unsigned int* ticket, long long nsb, long long ghost_block, long long* totals_a,
-                      long long* totals_b) {
+                      unsigned long long* chain, unsigned int* ticket, long long nsb, long long ghost_block,
+                      unsigned long long* ghost_words, long long* totals_a, long long* totals_b) {
   __shared__ unsigned long long wsum_v[SC_THREADS / 32], wsum_f[SC_THREADS / 32];
   __shared__ unsigned long long base_s[2];
   __shared__ unsigned sb;
@@ -332,6 +230,10 @@ mt_scan_blocks_kernel(const unsigned long long* __restrict__ raw, long long nblo
     if (i0 + k < nblocks) {
       st_relaxed(status + 2 * (i0 + k), FLAG_INC | pv);
       st_relaxed(status + 2 * (i0 + k) + 1, FLAG_INC | pf);
+      if (i0 + k == ghost_block) {  // (ghost_words are part of the scan state the classify kernel cleared)
+        st_relaxed(ghost_words, FLAG_INC | pv);
+        st_relaxed(ghost_words + 1, FLAG_INC | pf);
+      }
     }
   }
   if (b == nsb - 1 && threadIdx.x == 0) {
@@ -339,7 +241,7 @@ mt_scan_blocks_kernel(const unsigned long long* __restrict__ raw, long long nblo
     if (ghost_block >= 0) {  // written by a scan block with a lower (or this) ticket: it is running or done
       unsigned long long sv, sf;
       do {
-        sv = ld_relaxed(status + 2 * ghost_block), sf = ld_relaxed(status + 2 * ghost_block + 1);
+        sv = ld_relaxed(ghost_words), sf = ld_relaxed(ghost_words + 1);
       } while ((sv >> 62) != 2 || (sf >> 62) != 2);
       gv = sv & VAL_MASK, gf = sf & VAL_MASK;
     }

@@ -148,9 +148,12 @@ __device__ __forceinline__ float ldg_stream_f1(const float* p) {
 template <bool VEC, typename T = float>
 __global__ void __launch_bounds__(SP_WARPS * 32)
 signpack_kernel(const T* __restrict__ sdf, uint32_t* __restrict__ bits, int nx, int ny, int nz, long long ldx,
-                int W, T thresh, int nxseg, long long ntasks) {
+                int W, T thresh, int nxseg, long long ntasks, unsigned long long* __restrict__ clear, int nclear) {
   __shared__ __align__(16) uint32_t stage[SP_WARPS][SP_ZW][SP_XSEG];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  // block 0 resets the scan state (ticket + look-back chain) of the count/scan kernels that follow in the stream
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < nclear; i += blockDim.x) clear[i] = 0ull;
   const long long task = (long long)blockIdx.x * SP_WARPS + wib;
   if (task >= ntasks) return;
   const int xseg = (int)(task % nxseg);
@@ -425,43 +428,50 @@ __device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
   asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// one warp: lane r stores this rank's totals into rank r's buffer (a P2P store over NVLink for r != rank)
-__global__ void peer_publish_kernel(PeerSlots ps, int world, int rank, long long epoch, const long long* __restrict__ totals) {
-  const int r = threadIdx.x;
-  if (r >= world) return;
-  long long* s = ps.slot[r] + ((epoch & 1) * PEER_MAX + rank) * 4;
-  s[0] = totals[0], s[1] = totals[1], s[2] = 0;
-  st_release_sys(s + 3, epoch);
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
 }
-// one warp: lane r waits for rank r's totals of this epoch in the LOCAL buffer; bases[0..1] = exclusive prefix of
-// (nverts, nfaces) over the ranks below this one, bases[2..3] = grand totals; optionally all pairs to `all`.
-// A peer that never arrives trips the timeout (about a second) instead of hanging the GPU: *err = 1.
-__global__ void peer_gather_kernel(const long long* mine, int world, int rank, long long epoch, long long* __restrict__ bases,
-                                   long long* __restrict__ all, long long* err) {
+// One warp.  Lane r stores this rank's totals into rank r's buffer (a P2P store over NVLink for r != rank), then waits
+// for rank r's totals of this epoch in the LOCAL buffer; bases[0..1] = exclusive prefix of (nverts, nfaces) over the
+// ranks below this one, bases[2..3] = grand totals; optionally all pairs to `all`.  Every rank publishes before it
+// waits, so the ranks cannot block each other.  timeout_ns == 0 waits for ever (like an NCCL collective); otherwise
+// a peer that never arrives sets *err = 1 -- generate kernels behind this one then emit nothing -- and zero bases.
+__global__ void peer_exchange_kernel(PeerSlots ps, int world, int rank, long long epoch, const long long* __restrict__ totals,
+                                     long long* __restrict__ bases, long long* __restrict__ all, long long* err,
+                                     unsigned long long timeout_ns) {
   const int r = threadIdx.x;
   long long nv = 0, nf = 0;
   bool ok = true;
   if (r < world) {
-    const long long* s = mine + ((epoch & 1) * PEER_MAX + r) * 4;
-    long long spins = 0;
-    while (ld_acquire_sys(s + 3) != epoch) {
+    long long* s = ps.slot[r] + ((epoch & 1) * PEER_MAX + rank) * 4;
+    s[0] = totals[0], s[1] = totals[1], s[2] = 0;
+    st_release_sys(s + 3, epoch);
+    const long long* m = ps.slot[rank] + ((epoch & 1) * PEER_MAX + r) * 4;
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys(m + 3) != epoch) {
       __nanosleep(200);
-      if (++spins > 4000000) {
+      if (timeout_ns && global_timer_ns() - t0 > timeout_ns) {
         ok = false;
         break;
       }
     }
-    nv = s[0], nf = s[1];
-    if (all) all[2 * r] = nv, all[2 * r + 1] = nf;
+    if (ok) nv = m[0], nf = m[1];
   }
-  if (!__all_sync(0xffffffffu, ok) && r == 0) *err = 1;
+  const bool all_ok = __all_sync(0xffffffffu, ok);
+  if (!all_ok) nv = nf = 0;
+  if (r < world && all) all[2 * r] = nv, all[2 * r + 1] = nf;
   long long bv = r < rank ? nv : 0, bf = r < rank ? nf : 0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     bv += __shfl_xor_sync(0xffffffffu, bv, o), bf += __shfl_xor_sync(0xffffffffu, bf, o);
     nv += __shfl_xor_sync(0xffffffffu, nv, o), nf += __shfl_xor_sync(0xffffffffu, nf, o);
   }
-  if (r == 0) bases[0] = bv, bases[1] = bf, bases[2] = nv, bases[3] = nf;
+  if (r == 0) {
+    bases[0] = bv, bases[1] = bf, bases[2] = nv, bases[3] = nf;
+    if (!all_ok) *err = 1;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -518,8 +528,8 @@ __global__ void case_kernel(const uint32_t* __restrict__ bits, Grid g, uint8_t* 
 struct GenArgs {
   const void* sdf;  // Float32 field (Float64 for the *_f64 instantiations)
   const uint32_t* bits;
-  const unsigned long long* status;  // look-back chain state (MT / fused: inclusive prefixes per block)
-  const unsigned long long* woff;    // MC two-kernel form: exclusive (vertex, face) prefix of every generate block
+  const unsigned long long* status;  // MT: inclusive (vertex, face) prefix of every generate block
+  const unsigned long long* woff;    // MC: exclusive (vertex, face) prefix of every generate block
   const double* coords;              // xp | yp | zp
   void* verts;
   long long* faces;
@@ -532,11 +542,9 @@ struct GenArgs {
   double eps_d;
   int iso_is_f32, eps_is_f32, p_is_f32;  // typeof(iso), typeof(eps), eltype of the points (ranges)
   int sdf_vec;                           // Float32 field, base 16-byte aligned, ldx % 4 == 0: aligned pair loads
-  // fused single-pass kernels only: ticket counter, number of blocks, where the last block writes the totals
-  unsigned int* ticket;
   long long nblocks;
-  long long* totals_a;
-  long long* totals_b;
+  const long long* totals_a;     // device totals {nverts, nfaces} of the count
+  const long long* abort_flag;   // != 0: a peer exchange ahead of this kernel failed -- emit nothing
 };
 
 // Float64 field (MODE 3): everything is Float64 (src/marching_cubes.jl:100-104 with T = Float64).
@@ -583,9 +591,9 @@ constexpr int GEN_MAXF = GEN_NB * 5;    // faces of a round (MC: <= 5 per voxel)
 
 // Pushes the (y,z | case) records of this thread's active voxels whose position in the block's scan order
 // falls in [lo, hi).  `a0` = position of the thread's first active voxel, q = its (already loaded) quad-cell.
+// A record is one 8-byte store: .x = y | z << 16, .y = case index.
 template <int ALGO>
-__device__ __forceinline__ void push_records(const Quad& q, const TMap& tm, uint32_t a0, uint32_t lo, uint32_t hi,
-                                             uint32_t* rec_yz, uint8_t* rec_c) {
+__device__ __forceinline__ void push_records(const Quad& q, const TMap& tm, uint32_t a0, uint32_t lo, uint32_t hi, uint2* rec, int stride) {
   uint32_t idx = a0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -597,11 +605,8 @@ __device__ __forceinline__ void push_records(const Quad& q, const TMap& tm, uint
     while (mm) {
       const int k = __ffs(mm) - 1;
       mm &= mm - 1;
-      if (idx >= lo && idx < hi) {
-        const uint32_t s = idx - lo;
-        rec_yz[s] = (uint32_t)tm.y | ((uint32_t)((tm.zq * 4 + i) * 32 + k) << 16);
-        rec_c[s] = (uint8_t)case_of<ALGO>(q, i, k);
-      }
+      if (idx >= lo && idx < hi)
+        rec[(idx - lo) * stride] = make_uint2((uint32_t)tm.y | ((uint32_t)((tm.zq * 4 + i) * 32 + k) << 16), case_of<ALGO>(q, i, k));
       ++idx;
     }
   }
@@ -617,53 +622,43 @@ __device__ __forceinline__ uint32_t count_active(const uint32_t* __restrict__ bi
   return na;
 }
 
-// Block id: FUSED kernels take a ticket (blocks must be numbered in an order in which every predecessor
-// has already started, for the look-back chain); the others use blockIdx.
-template <bool FUSED>
-__device__ __forceinline__ unsigned block_id(unsigned int* ticket, unsigned* s_b) {
-  if (!FUSED) return blockIdx.x;
-  if (threadIdx.x == 0) *s_b = atomicAdd(ticket, 1u);
-  __syncthreads();
-  return *s_b;
+// samples (x, x+1) of a row whose element x - (x & 3) is 16-byte aligned; ph = x & 3
+__device__ __forceinline__ float2 pair_load(const float* p, int ph) {
+  if (ph == 0 || ph == 2) return __ldg(reinterpret_cast<const float2*>(p));
+  if (ph == 1) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p - 1));
+    return make_float2(v.y, v.z);
+  }
+  const float2 lo = __ldg(reinterpret_cast<const float2*>(p - 1)), hi = __ldg(reinterpret_cast<const float2*>(p + 1));
+  return make_float2(lo.y, hi.x);
 }
 
-// Exclusive prefixes (vertices, faces) of block b in the whole mesh.
-//   !FUSED: count_kernel ran before and left the inclusive prefixes in `status`.
-//    FUSED: this block publishes its own totals and looks back (warp 0), everyone else waits at the barrier.
-template <bool FUSED>
-__device__ __forceinline__ void block_base(const GenArgs& a, unsigned b, unsigned long long tot_v, unsigned long long tot_f,
-                                           unsigned long long* s_base, unsigned long long& bv, unsigned long long& bf) {
-  if (!FUSED) {  // exclusive prefixes of every generate block, written by mc_count_warp_kernel
-    bv = a.woff[2 * (unsigned long long)b];
-    bf = a.woff[2 * (unsigned long long)b + 1];
-    return;
-  }
-  if (threadIdx.x < 32) {
-    unsigned long long ev, ef;
-    lookback(const_cast<unsigned long long*>(a.status), (long long)b, tot_v, tot_f, ev, ef);
-    if (threadIdx.x == 0) {
-      s_base[0] = ev, s_base[1] = ef;
-      if ((long long)b == a.nblocks - 1) {
-        a.totals_a[0] = (long long)(ev + tot_v), a.totals_a[1] = (long long)(ef + tot_f);
-        if (a.totals_b) a.totals_b[0] = (long long)(ev + tot_v), a.totals_b[1] = (long long)(ef + tot_f);
-      }
+// The four samples of one z-plane of a voxel: (x,y) (x+1,y) (x,y+1) (x+1,y+1).
+template <class T>
+struct Plane {
+  T a00, a10, a01, a11;
+};
+template <class T>
+__device__ __forceinline__ Plane<T> load_plane(const T* p, long long ldx, int ph, bool vec) {
+  Plane<T> r;
+  if constexpr (sizeof(T) == 4) {
+    if (vec) {
+      // Float32 field with 16-byte aligned rows: the (x, x+1) pair of a row is ONE aligned load (two when it
+      // straddles a 16-byte boundary); x is uniform over the block, so the switch does not diverge
+      const float2 q0 = pair_load(reinterpret_cast<const float*>(p), ph), q1 = pair_load(reinterpret_cast<const float*>(p) + ldx, ph);
+      r.a00 = q0.x, r.a10 = q0.y, r.a01 = q1.x, r.a11 = q1.y;
+      return r;
     }
   }
-  __syncthreads();
-  bv = s_base[0], bf = s_base[1];
+  r.a00 = __ldg(p), r.a10 = __ldg(p + 1), r.a01 = __ldg(p + ldx), r.a11 = __ldg(p + ldx + 1);
+  return r;
 }
-
-// samples (x, x+1) of a row whose element x - (x & 3) is 16-byte aligned; ph = x & 3
-__device__ __forceinline__ void pair_load(const float* p, int ph, float2& out) {
-  if (ph == 0 || ph == 2) {
-    out = __ldg(reinterpret_cast<const float2*>(p));
-  } else if (ph == 1) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(p - 1));
-    out = make_float2(v.y, v.z);
-  } else {
-    const float2 lo = __ldg(reinterpret_cast<const float2*>(p - 1)), hi = __ldg(reinterpret_cast<const float2*>(p + 1));
-    out = make_float2(lo.y, hi.x);
-  }
+template <class T>
+__device__ __forceinline__ Plane<T> shfl_up_plane(const Plane<T>& v) {
+  Plane<T> r;
+  r.a00 = __shfl_up_sync(0xffffffffu, v.a00, 1), r.a10 = __shfl_up_sync(0xffffffffu, v.a10, 1);
+  r.a01 = __shfl_up_sync(0xffffffffu, v.a01, 1), r.a11 = __shfl_up_sync(0xffffffffu, v.a11, 1);
+  return r;
 }
 
 template <int MODE>
@@ -675,178 +670,178 @@ struct FieldOf<3> {
   using type = double;
 };
 
-// FUSED = false: generate after count_kernel (two-phase ABI: the caller sizes its arrays in between).
-// FUSED = true : classify-output -> mesh in ONE pass: count, decoupled look-back scan and generate fused
-//                (outputs must have capacity; totals are written by the last block).
-template <int MODE, typename V, bool FUSED>
+// Three consecutive output scalars of element `gi` (a vertex: 3 V; a face: 3 Int64) as one 2-wide and one 1-wide
+// store instead of three: elements are 12 / 24 bytes, so the 2-wide half is the one that is naturally aligned.
+// Fewer store requests = fewer L1 line look-ups (the kernel is bound by those).
+template <class S>
+__device__ __forceinline__ void store3(S* base, long long gi, S v0, S v1, S v2, bool wide_ok) {
+  S* o = base + 3 * gi;
+  if (wide_ok) {
+    struct alignas(2 * sizeof(S)) S2 {
+      S a, b;
+    };
+    if ((gi & 1) == 0) {
+      *reinterpret_cast<S2*>(o) = S2{v0, v1};
+      o[2] = v2;
+    } else {
+      o[0] = v0;
+      *reinterpret_cast<S2*>(o + 1) = S2{v1, v2};
+    }
+  } else {
+    o[0] = v0, o[1] = v1, o[2] = v2;
+  }
+}
+
+// generate after the count (two-phase ABI: the caller sizes its arrays in between; the async form runs them back to back).
+//
+// Shared-memory record of an active voxel (16 bytes, read by the vertex threads with ONE 128-bit load):
+//   .x = y | z << 16          .y = local vertex offset | local face offset << 16
+//   .z/.w = the voxel's ordered edge list (nibbles 0..7 / 8..11 of ISO_MC_VERTS[case])
+// plus its packed face list (ISO_MC_FACES[case]) in recf[].  The per-case tables are read once per voxel (B1b) --
+// not once per vertex and once per face: each of those was a 32-address gather into a 2 KB table, i.e. up to 16 L1
+// line look-ups per warp instruction, and the kernel is bound by L1 line look-ups.
+template <int MODE, typename V>
 __global__ void __launch_bounds__(CB_THREADS, ISO_GEN_MINB)
 mc_generate_kernel(GenArgs a, Grid g) {
-// per-case tables straight from global memory through L1 (4 KB, hot in every SM): staging them in shared memory
-// per block cost more than it saved (generate 0.741 -> 0.726 ms at 1024^3); -DISO_GEN_SMEM_TABLES restores the staging
-#ifndef ISO_GEN_SMEM_TABLES
-#define tabV(i) __ldg(&ISO_MC_VERTS[i])
-#define tabF(i) __ldg(&ISO_MC_FACES[i])
-#else
-  __shared__ unsigned long long tabV_s[256], tabF_s[256];
-#define tabV(i) tabV_s[i]
-#define tabF(i) tabF_s[i]
-#endif
-  __shared__ unsigned long long s_base[2];
   __shared__ uint32_t s_w[CB_THREADS / 32];
-  __shared__ unsigned s_b;
-  __shared__ uint32_t rec_yz[GEN_NB];
-  __shared__ uint32_t rec_pk[GEN_NB];  // case | local vertex offset << 8 | local face offset << 20
-  __shared__ uint8_t rec_c[GEN_NB];
+  __shared__ __align__(16) uint4 rec[GEN_NB];
+  __shared__ unsigned long long recf[GEN_NB];
   using T = typename FieldOf<MODE>::type;  // Float32, or Float64 for MODE 3
   __shared__ __align__(16) T corner[GEN_NB][8];
   __shared__ uint8_t owner_v[GEN_MAXV], owner_f[GEN_MAXF];
-  __shared__ uint8_t edge_c[12];
 
   const int tid = threadIdx.x;
-  const unsigned b = block_id<FUSED>(a.ticket, &s_b);
-  if (!FUSED) {
-    // the count kernel left every block's exclusive prefix: a block whose successor starts at the same vertex has
+  const unsigned b = blockIdx.x;
+  if (a.abort_flag && *a.abort_flag) return;  // the exchange that was to deliver the vertex base failed
+  unsigned long long bv, bf;
+  {
+    // the count left every block's exclusive prefix: a block whose successor starts at the same vertex has
     // no active voxel (each one emits >= 3 vertices) -- leave before touching the bit-field.  On sparse fields
     // (a few shapes in a big volume) that is most blocks.
-    const unsigned long long v0 = a.woff[2 * (unsigned long long)b];
+    bv = a.woff[2 * (unsigned long long)b];
     const unsigned long long v1 = (long long)b + 1 < a.nblocks ? a.woff[2 * ((unsigned long long)b + 1)] : (unsigned long long)a.totals_a[0];
-    if (v0 == v1) return;
+    if (bv == v1) return;
+    bf = a.woff[2 * (unsigned long long)b + 1];
   }
-#ifdef ISO_GEN_PLAIN_DIV
-  const TMap tm = thread_map_div(g, b);
-#else
   const TMap tm = thread_map(g, b);
-#endif
   // ---- A: active voxels per thread, exclusive scan (thread order == scan order) ----
   Quad q;
   const uint32_t tna = count_active(a.bits, g, tm, q);
   uint32_t blk_na;
   const uint32_t my_a0 = block_excl_scan_u32(tna, s_w, blk_na);
-  if (blk_na == 0) {  // uniform: nothing crosses this block
-    if (FUSED) {
-      unsigned long long bv, bf;
-      block_base<true>(a, b, 0, 0, s_base, bv, bf);
-    }
-    return;
-  }
-#ifdef ISO_GEN_SMEM_TABLES
-  for (int i = tid; i < 256; i += CB_THREADS) tabV_s[i] = ISO_MC_VERTS[i], tabF_s[i] = ISO_MC_FACES[i];
-#endif
-  if (tid < 12) edge_c[tid] = ISO_MC_EDGE_CORNERS[tid];
+  if (blk_na == 0) return;  // (cannot happen after the test above; kept as a guard)
 
-  unsigned long long bv = 0, bf = 0;
-  bool have_base = false;
-  if (!FUSED) {
-    block_base<false>(a, b, 0, 0, s_base, bv, bf);
-    have_base = true;
-  } else if (blk_na > (uint32_t)GEN_NB) {
-    // several windows: the block totals are needed before anything can be emitted -> counting pre-pass
-    __syncthreads();  // tables
-    uint32_t tv = 0, tf = 0;
-    for (uint32_t lo = 0; lo < blk_na; lo += GEN_NB) {
-      const uint32_t hi = min(lo + (uint32_t)GEN_NB, blk_na);
-      if (tna && my_a0 < hi && my_a0 + tna > lo) push_records<0>(q, tm, my_a0, lo, hi, rec_yz, rec_c);
-      __syncthreads();
-      for (uint32_t s = tid; s < hi - lo; s += CB_THREADS) {
-        const unsigned long long t = tabV(rec_c[s]);
-        tv += (uint32_t)((t >> 48) & 15), tf += (uint32_t)((t >> 52) & 7);
-      }
-      __syncthreads();
-    }
-    uint32_t totv, totf;  // (block totals can exceed 16 bits per field: reduce the two fields separately)
-    block_excl_scan_u32(tv, s_w, totv);
-    block_excl_scan_u32(tf, s_w, totf);
-    block_base<true>(a, b, totv, totf, s_base, bv, bf);
-    have_base = true;
-  }
   const long long vbase = a.vbase + (a.vbase_dev ? *a.vbase_dev : 0);
   const unsigned yofs = (unsigned)g.nx, zofs = (unsigned)(g.nx + g.ny);  // coords = xp | yp | zp
   const double x0d = __ldg(a.coords + tm.x), x1d = __ldg(a.coords + tm.x + 1);
   V* verts = reinterpret_cast<V*>(a.verts);
   const int x = tm.x;
+  const int lane = tid & 31;
+  const bool vwide = (reinterpret_cast<uintptr_t>(a.verts) & (2 * sizeof(V) - 1)) == 0;
+  const bool fwide = (reinterpret_cast<uintptr_t>(a.faces) & 15) == 0;
+
+  // ---- B1a: records (position, case) of the window's voxels, in scan order; the case index of an active voxel is
+  //      computed exactly once, here.  The first window (the only one unless the block holds more than GEN_NB
+  //      active voxels) is pushed from the quad-cell in registers, which is dead afterwards; later windows reload it.
+  if (tna && my_a0 < (uint32_t)GEN_NB) push_records<0>(q, tm, my_a0, 0, min((uint32_t)GEN_NB, blk_na), reinterpret_cast<uint2*>(rec), 2);
 
   for (uint32_t lo = 0; lo < blk_na; lo += GEN_NB) {
     const uint32_t hi = min(lo + (uint32_t)GEN_NB, blk_na);
     const uint32_t cnt = hi - lo;
-    // ---- B1a: records (position, case) of the window's voxels, in scan order; the case index of an
-    //      active voxel is computed exactly once, here ----
-    if (tna && my_a0 < hi && my_a0 + tna > lo) push_records<0>(q, tm, my_a0, lo, hi, rec_yz, rec_c);
+    if (lo > 0 && tna && my_a0 < hi && my_a0 + tna > lo) {
+      Quad q2;
+      load_quad(a.bits, g, tm.x, tm.y, tm.zq, q2);
+      push_records<0>(q2, tm, my_a0, lo, hi, reinterpret_cast<uint2*>(rec), 2);
+    }
     __syncthreads();
-    // ---- B1b: two records per thread: counts -> scan -> owner maps; gather the 8 corner samples ----
+    // ---- B1b: two records per thread: tables -> counts -> scan -> owner maps; gather the corner samples.
+    // z-adjacent records (same column, z + 1: adjacent in scan order) share a sample plane: the lower plane of the
+    // second is the upper plane of the first -- taken from registers (in-thread pair) or from the lane below
+    // (shuffle) instead of being gathered again.
     const uint32_t r0 = 2 * tid, r1 = r0 + 1;
-    uint32_t nv0 = 0, nf0 = 0, nv1 = 0, nf1 = 0;
+    uint32_t nvf0 = 0, nvf1 = 0;  // vertices | faces << 16 of the two records
+    uint32_t yz0 = 0xffffffffu, yz1 = 0xfffffffeu;
     if (r0 < cnt) {
-      const unsigned long long tv = tabV(rec_c[r0]);
-      nv0 = (uint32_t)((tv >> 48) & 15), nf0 = (uint32_t)((tv >> 52) & 7);
+      const uint2 rc = *reinterpret_cast<const uint2*>(&rec[r0]);
+      yz0 = rc.x;
+      const unsigned long long tv = __ldg(&ISO_MC_VERTS[rc.y]);
+      recf[r0] = __ldg(&ISO_MC_FACES[rc.y]);
+      *reinterpret_cast<uint2*>(&rec[r0].z) = make_uint2((uint32_t)tv, (uint32_t)(tv >> 32) & 0xffffu);
+      nvf0 = (uint32_t)((tv >> 48) & 15) | ((uint32_t)((tv >> 52) & 7) << 16);
     }
     if (r1 < cnt) {
-      const unsigned long long tv = tabV(rec_c[r1]);
-      nv1 = (uint32_t)((tv >> 48) & 15), nf1 = (uint32_t)((tv >> 52) & 7);
+      const uint2 rc = *reinterpret_cast<const uint2*>(&rec[r1]);
+      yz1 = rc.x;
+      const unsigned long long tv = __ldg(&ISO_MC_VERTS[rc.y]);
+      recf[r1] = __ldg(&ISO_MC_FACES[rc.y]);
+      *reinterpret_cast<uint2*>(&rec[r1].z) = make_uint2((uint32_t)tv, (uint32_t)(tv >> 32) & 0xffffu);
+      nvf1 = (uint32_t)((tv >> 48) & 15) | ((uint32_t)((tv >> 52) & 7) << 16);
     }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const uint32_t rr = r0 + r;
-      if (rr < cnt) {
-        const uint32_t yz = rec_yz[rr];
-        const T* p = reinterpret_cast<const T*>(a.sdf) + x + g.ldx * (long long)(yz & 0xffffu) + g.plane * (long long)(yz >> 16);
-        T c0, c1, c2, c3, c4, c5, c6, c7;
-        if (sizeof(T) == 4 && a.sdf_vec) {
-          // Float32 field with 16-byte aligned rows: the (x, x+1) pair of each of the 4 rows comes from ONE aligned
-          // load (two when it straddles a 16-byte boundary) -- x is uniform over the block, no divergence.
-          // Fewer LSU sector accesses than 8 scalar gathers (the generate kernel is LSU-bound).
-          const float* r0 = reinterpret_cast<const float*>(p);
-          const float* r1 = r0 + g.ldx;
-          const float* r2 = r0 + g.plane;
-          const float* r3 = r2 + g.ldx;
-          float2 q0, q1, q2, q3;
-          pair_load(r0, x & 3, q0), pair_load(r1, x & 3, q1), pair_load(r2, x & 3, q2), pair_load(r3, x & 3, q3);
-          c0 = (T)q0.x, c1 = (T)q0.y, c3 = (T)q1.x, c2 = (T)q1.y, c4 = (T)q2.x, c5 = (T)q2.y, c7 = (T)q3.x, c6 = (T)q3.y;
-        } else {
-          c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + g.ldx + 1), c3 = __ldg(p + g.ldx);
-          const T* p1 = p + g.plane;
-          c4 = __ldg(p1), c5 = __ldg(p1 + 1), c6 = __ldg(p1 + g.ldx + 1), c7 = __ldg(p1 + g.ldx);
-        }
-        corner[rr][0] = c0, corner[rr][1] = c1, corner[rr][2] = c2, corner[rr][3] = c3;
-        corner[rr][4] = c4, corner[rr][5] = c5, corner[rr][6] = c6, corner[rr][7] = c7;
+    {
+      const bool vec = sizeof(T) == 4 && a.sdf_vec;
+      const int ph = x & 3;
+      const T* fld = reinterpret_cast<const T*>(a.sdf) + x;
+      const uint32_t pyz1 = __shfl_up_sync(0xffffffffu, yz1, 1);
+      const bool adj0 = lane > 0 && r0 < cnt && yz0 == pyz1 + 0x10000u;  // r0 continues the z-run of the lane below
+      const bool adj1 = r1 < cnt && yz1 == yz0 + 0x10000u;                // r1 continues r0's run
+      Plane<T> L0{}, U0{}, L1{}, U1{};
+      if (r0 < cnt) {
+        const T* p = fld + g.ldx * (long long)(yz0 & 0xffffu) + g.plane * (long long)(yz0 >> 16);
+        if (!adj0) L0 = load_plane<T>(p, g.ldx, ph, vec);
+        U0 = load_plane<T>(p + g.plane, g.ldx, ph, vec);
+      }
+      if (r1 < cnt) {
+        const T* p = fld + g.ldx * (long long)(yz1 & 0xffffu) + g.plane * (long long)(yz1 >> 16);
+        if (!adj1) L1 = load_plane<T>(p, g.ldx, ph, vec);
+        U1 = load_plane<T>(p + g.plane, g.ldx, ph, vec);
+      }
+      const Plane<T> below = shfl_up_plane<T>(U1);  // (all lanes take part)
+      if (adj0) L0 = below;
+      if (adj1) L1 = U0;
+      // MC corner order (src/marching_cubes.jl:42-49): 0 (0,0,0) 1 (1,0,0) 2 (1,1,0) 3 (0,1,0), then the same at z + 1
+      if (r0 < cnt) {
+        corner[r0][0] = L0.a00, corner[r0][1] = L0.a10, corner[r0][2] = L0.a11, corner[r0][3] = L0.a01;
+        corner[r0][4] = U0.a00, corner[r0][5] = U0.a10, corner[r0][6] = U0.a11, corner[r0][7] = U0.a01;
+      }
+      if (r1 < cnt) {
+        corner[r1][0] = L1.a00, corner[r1][1] = L1.a10, corner[r1][2] = L1.a11, corner[r1][3] = L1.a01;
+        corner[r1][4] = U1.a00, corner[r1][5] = U1.a10, corner[r1][6] = U1.a11, corner[r1][7] = U1.a01;
       }
     }
     uint32_t wtot;
-    const uint32_t ex = block_excl_scan_u32((nv0 + nv1) | ((nf0 + nf1) << 16), s_w, wtot);
+    const uint32_t ex = block_excl_scan_u32(nvf0 + nvf1, s_w, wtot);
     {
       const uint32_t v0 = ex & 0xffffu, f0 = ex >> 16;
+      const uint32_t nv0 = nvf0 & 0xffffu, nf0 = nvf0 >> 16, nv1 = nvf1 & 0xffffu, nf1 = nvf1 >> 16;
       if (r0 < cnt) {
-        rec_pk[r0] = (uint32_t)rec_c[r0] | (v0 << 8) | (f0 << 20);
+        rec[r0].y = ex;  // local vertex offset | local face offset << 16
         for (uint32_t i = 0; i < nv0; ++i) owner_v[v0 + i] = (uint8_t)r0;
         for (uint32_t i = 0; i < nf0; ++i) owner_f[f0 + i] = (uint8_t)r0;
       }
       if (r1 < cnt) {
-        rec_pk[r1] = (uint32_t)rec_c[r1] | ((v0 + nv0) << 8) | ((f0 + nf0) << 20);
+        rec[r1].y = ex + nvf0;
         for (uint32_t i = 0; i < nv1; ++i) owner_v[v0 + nv0 + i] = (uint8_t)r1;
         for (uint32_t i = 0; i < nf1; ++i) owner_f[f0 + nf0 + i] = (uint8_t)r1;
       }
     }
     const uint32_t nvr = wtot & 0xffffu, nfr = wtot >> 16;
-    if (FUSED && !have_base) {  // single window: its totals are the block totals
-      block_base<true>(a, b, nvr, nfr, s_base, bv, bf);
-      have_base = true;
-    } else {
-      __syncthreads();
-    }
+    __syncthreads();
 
     // capacity guard hoisted: the whole window fits in the output buffers in all but the overflow case
     const bool vfits = (long long)bv + nvr <= a.vcap, ffits = (long long)bf + nfr <= a.fcap;
     // ---- B2: thread per vertex (vertex_interp, src/marching_cubes.jl:100-104) ----
     for (uint32_t k = tid; k < nvr; k += CB_THREADS) {
       const uint32_t s = owner_v[k];  // record index 0..255
-      const uint32_t pk = rec_pk[s], yz = rec_yz[s];
-      const uint32_t which = k - ((pk >> 8) & 0xfffu);
-      const uint32_t e = (uint32_t)(tabV(pk & 0xffu) >> (4 * which)) & 15u;
-      const uint32_t cc = edge_c[e];
-      const uint32_t ca = cc & 15u, cb = cc >> 4;
+      const uint4 r = rec[s];
+      const uint32_t which = k - (r.y & 0xffffu);
+      const uint32_t e = ((which < 8 ? r.z >> (4 * which) : r.w >> (4 * which - 32)) & 15u);
+      // _mc_edge_list (src/lut/mc.jl:606-608), 0-based: edge e runs from corner e & 7 to corner
+      // (e & 4) | ((e + 1) & 3) for the 8 in-plane edges and to corner e - 4 for the 4 vertical ones
+      const uint32_t ca = e & 7u, cb = e < 8u ? ((e & 4u) | ((e + 1u) & 3u)) : e - 4u;
       // MC corner offsets (dx | dy<<1 | dz<<2) for corners 0..7: 0,1,3,2,4,5,7,6
       const uint32_t oa = (0x67542310u >> (4 * ca)) & 7u, ob = (0x67542310u >> (4 * cb)) & 7u;
       const T va = corner[s][ca], vb = corner[s][cb];
-      const unsigned vy = yofs + (yz & 0xffffu), vz = zofs + (yz >> 16);
+      const unsigned vy = yofs + (r.x & 0xffffu), vz = zofs + (r.x >> 16);
       double pa[3], pb[3];
       pa[0] = (oa & 1u) ? x1d : x0d;
       pa[1] = __ldg(a.coords + (vy + ((oa >> 1) & 1u)));
@@ -859,28 +854,22 @@ mc_generate_kernel(GenArgs a, Grid g) {
       double p[3];
       if constexpr (MODE == 3) mc_interp_f64(a, va, vb, pa, pb, p);
       else mc_interp<MODE>(a, va, vb, pa, pb, p);
-      if (vfits || (long long)bv + k < a.vcap) {
-        V* o = verts + 3 * ((long long)bv + k);
-        o[0] = (V)p[0], o[1] = (V)p[1], o[2] = (V)p[2];
-      }
+      if (vfits || (long long)bv + k < a.vcap) store3<V>(verts, (long long)bv + k, (V)p[0], (V)p[1], (V)p[2], vwide);
     }
     // ---- B3: thread per face ----
     for (uint32_t k = tid; k < nfr; k += CB_THREADS) {
-      const uint32_t pk = rec_pk[owner_f[k]];
-      const uint32_t fi = k - (pk >> 20);
-      const uint32_t tri = (uint32_t)(tabF(pk & 0xffu) >> (12 * fi)) & 0xfffu;
-      const long long fct = vbase + (long long)bv + ((pk >> 8) & 0xfffu) + 1;  // 1-based index of the voxel's first vertex
-      if (ffits || (long long)bf + k < a.fcap) {
-        long long* o = a.faces + 3 * ((long long)bf + k);
-        o[0] = fct + (tri & 15u), o[1] = fct + ((tri >> 4) & 15u), o[2] = fct + ((tri >> 8) & 15u);
-      }
+      const uint32_t s = owner_f[k];
+      const uint32_t ry = rec[s].y;
+      const uint32_t fi = k - (ry >> 16);
+      const uint32_t tri = (uint32_t)(recf[s] >> (12 * fi)) & 0xfffu;
+      const long long fct = vbase + (long long)bv + (ry & 0xffffu) + 1;  // 1-based index of the voxel's first vertex
+      if (ffits || (long long)bf + k < a.fcap)
+        store3<long long>(a.faces, (long long)bf + k, fct + (tri & 15u), fct + ((tri >> 4) & 15u), fct + ((tri >> 8) & 15u), fwide);
     }
     bv += nvr, bf += nfr;  // next window continues where this one ended
     __syncthreads();
   }
 }
-#undef tabV
-#undef tabF
 
 // faces[0 .. 3*min(totals[1], fcap)) += *base   (sharded fix-up after the all-gather of the slab totals)
 __global__ void add_base_kernel(long long* __restrict__ faces, long long fcap, const long long* __restrict__ totals,

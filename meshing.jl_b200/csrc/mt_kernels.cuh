@@ -130,8 +130,8 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
   __shared__ uint16_t einfo_s[20];
   __shared__ uint8_t eshift_s[160];
   __shared__ uint32_t s_w[CB_THREADS / 32];
-  __shared__ uint32_t rec_yz[MTG_NB], rec_vc[MTG_NB], rec_f[MTG_NB];
-  __shared__ uint8_t rec_c[MTG_NB];
+  __shared__ uint2 rec_yc[MTG_NB];  // .x = y | z << 16, .y = case index
+  __shared__ uint32_t rec_vc[MTG_NB], rec_f[MTG_NB];
   __shared__ int32_t evid[MTG_NB * MTG_EDGES];  // vertex id of each crossed edge, relative to the block's first vertex
   __shared__ uint8_t owner_v[MTG_MAXV];
   __shared__ uint8_t owner_f[MTG_MAXF];
@@ -139,6 +139,7 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
   const int tid = threadIdx.x;
 
   const unsigned b = blockIdx.x;
+  if (a.abort_flag && *a.abort_flag) return;  // the exchange that was to deliver the vertex base failed
   const TMap tm = thread_map_div(g, b);
   const int x = tm.x;
   if (g.ghost && x == 0) return;  // ghost row of an MT slab: its faces and vertices belong to the previous slab
@@ -206,13 +207,13 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
     if (tna && my_a0 < hi && my_a0 + tna > lo) {
       Quad qp;
       load_quad(a.bits, g, tm.x, tm.y, tm.zq, qp);
-      push_records<1>(qp, tm, my_a0, lo, hi, rec_yz, rec_c);
+      push_records<1>(qp, tm, my_a0, lo, hi, rec_yc, 1);
     }
     __syncthreads();
     // ---- B1b: thread per voxel: counts -> scan -> owner maps ----
     uint32_t nv = 0, nf = 0;
     if ((uint32_t)tid < cnt) {
-      const uint32_t c = rec_c[tid], yz = rec_yz[tid];
+      const uint32_t c = rec_yc[tid].y, yz = rec_yc[tid].x;
       const int flags = fx | ((yz & 0xffffu) == 0 ? 2 : 0) | ((yz >> 16) == 0 ? 4 : 0);
       nv = nown_of(c, flags), nf = MT_NF_S(c);
     }
@@ -220,7 +221,7 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
     const uint32_t ex = block_excl_scan_u32(nv | (nf << 16), s_w, wtot);
     if ((uint32_t)tid < cnt) {
       const uint32_t v0 = ex & 0xffffu, f0 = ex >> 16;
-      rec_vc[tid] = (wv + v0) | ((uint32_t)rec_c[tid] << 24);  // vertex offset relative to the block's first vertex
+      rec_vc[tid] = (wv + v0) | (rec_yc[tid].y << 24);  // vertex offset relative to the block's first vertex
       rec_f[tid] = f0;
       for (uint32_t i = 0; i < nv; ++i) owner_v[v0 + i] = (uint8_t)tid;
       for (uint32_t i = 0; i < nf; ++i) owner_f[f0 + i] = (uint8_t)tid;
@@ -230,7 +231,7 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
     // ---- B1c: thread per (voxel, crossed edge): resolve the vertex id through the owner voxel ----
     for (uint32_t it = tid; it < cnt * MTG_EDGES; it += CB_THREADS) {
       const uint32_t s = it / MTG_EDGES, j = it - s * MTG_EDGES;
-      const uint32_t vc = rec_vc[s], yz = rec_yz[s];
+      const uint32_t vc = rec_vc[s], yz = rec_yc[s].x;
       const uint32_t c = vc >> 24;
       const uint32_t cm = MT_CROSS_S(c);
       if (j >= (uint32_t)__popc(cm)) continue;
@@ -283,7 +284,7 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
     // ---- B2: thread per vertex (vertPos, src/marching_tetrahedra.jl:42-55) ----
     for (uint32_t k = tid; k < nvr; k += CB_THREADS) {
       const uint32_t s = owner_v[k];
-      const uint32_t vc = rec_vc[s], yz = rec_yz[s];
+      const uint32_t vc = rec_vc[s], yz = rec_yc[s].x;
       const uint32_t c = vc >> 24;
       const int vy = (int)(yz & 0xffffu), vz = (int)(yz >> 16);
       const int flags = fx | (vy == 0 ? 2 : 0) | (vz == 0 ? 4 : 0);

@@ -61,10 +61,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 
 __global__ void __launch_bounds__(TM_WARPS * 32)
 signpack_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t* __restrict__ bits, int nx, int ny, int nz, int W,
-                    float thresh, int nxseg, long long ntasks) {
+                    float thresh, int nxseg, long long ntasks, unsigned long long* __restrict__ clear, int nclear) {
   extern __shared__ __align__(128) unsigned char tm_smem[];
   __shared__ __align__(8) uint64_t full[TM_WARPS][TM_STAGES];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  // block 0 resets the scan state (ticket + look-back chain) of the count/scan kernels that follow in the stream
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < nclear; i += blockDim.x) clear[i] = 0ull;
   const long long task = (long long)blockIdx.x * TM_WARPS + wib;
   if (task >= ntasks) return;
   unsigned char* base = tm_smem + (128 - (smem_u32(tm_smem) & 127)) % 128 + (size_t)wib * TM_SMEM_PER_WARP;

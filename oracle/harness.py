@@ -34,6 +34,8 @@ def lib():
         i64, dbl, vp, ci = ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_int
         L.oracle_isosurface.restype = vp
         L.oracle_isosurface.argtypes = [ci, vp, ci, i64, i64, i64, dbl, ci, dbl, ci, dbl, dbl, dbl, dbl, dbl, dbl, ci, ci, i64, i64]
+        L.oracle_isosurface_slab.restype = vp
+        L.oracle_isosurface_slab.argtypes = [ci, vp, ci, i64, i64, i64, dbl, ci, dbl, ci, dbl, dbl, dbl, dbl, dbl, dbl, ci, ci, i64, i64]
         L.oracle_nverts.restype = i64
         L.oracle_nverts.argtypes = [vp]
         L.oracle_nfaces.restype = i64
@@ -67,10 +69,13 @@ def _field(sdf):
 
 
 def isosurface(sdf, algo=MC, iso=0.0, iso_is_f32=False, eps=1e-3, eps_is_f32=False,
-               ranges=None, range_kind=RANGE_INT, nthreads=1, xrange=None, copy=True):
+               ranges=None, range_kind=RANGE_INT, nthreads=1, xrange=None, copy=True, slab=None):
     """Oracle isosurface.  `ranges` = ((x0,x1),(y0,y1),(z0,z1)) endpoints (default (-1,1)^3).
     `xrange` = (xlo, xhi) restricts the sweep to voxel x-planes [xlo, xhi) (bounded bench sample; face
     indices are then relative to the first vertex of the range).  `copy=False` returns only the counts.
+    `slab` = (x_offset, nx_global), Marching Cubes only: `sdf` holds samples [x_offset, x_offset + nx) of a volume
+    with nx_global samples along x; vertices get the coordinates of the whole volume (`ranges` are the whole
+    volume's), face indices are relative to the slab's first vertex.
     Returns (vertices[nv,3] float32|float64, faces[nf,3] int64 1-based)."""
     a = sdf if (isinstance(sdf, np.ndarray) and sdf.flags.f_contiguous) else _field(sdf)
     xlo, xhi = xrange if xrange is not None else (-1, -1)
@@ -79,8 +84,13 @@ def isosurface(sdf, algo=MC, iso=0.0, iso_is_f32=False, eps=1e-3, eps_is_f32=Fal
         ranges = ((-1.0, 1.0),) * 3
     (x0, x1), (y0, y1), (z0, z1) = ranges
     L = lib()
-    h = L.oracle_isosurface(algo, a.ctypes.data, int(a.dtype == np.float64), nx, ny, nz, float(iso), int(iso_is_f32),
-                            float(eps), int(eps_is_f32), x0, x1, y0, y1, z0, z1, range_kind, nthreads, xlo, xhi)
+    if slab is not None:
+        assert algo == MC and xrange is None
+        h = L.oracle_isosurface_slab(algo, a.ctypes.data, int(a.dtype == np.float64), nx, ny, nz, float(iso), int(iso_is_f32),
+                                     float(eps), int(eps_is_f32), x0, x1, y0, y1, z0, z1, range_kind, nthreads, int(slab[0]), int(slab[1]))
+    else:
+        h = L.oracle_isosurface(algo, a.ctypes.data, int(a.dtype == np.float64), nx, ny, nz, float(iso), int(iso_is_f32),
+                                float(eps), int(eps_is_f32), x0, x1, y0, y1, z0, z1, range_kind, nthreads, xlo, xhi)
     try:
         nv, nf = L.oracle_nverts(h), L.oracle_nfaces(h)
         if not copy:

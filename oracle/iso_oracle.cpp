@@ -40,13 +40,16 @@ namespace {
 
 // LinRange{P}(a, b, n)[i] (0-based i here) == lerpi(i, max(n-1,1), a, b) = P((1-t)*a + t*b), t = i/d
 // evaluated in Float64 (base/range.jl, Julia >= 1.9).
+// `off`: the array handed to the oracle holds samples [off, off + nx) of a volume with n samples along this axis
+// (slab-wise parity of volumes too big for the host: Marching Cubes carries no state between voxels, so the sweep
+// of a slab with the WHOLE volume's coordinates is exactly that part of the whole sweep).
 template <class P>
 struct LinRange {
   P a, b;
-  int64_t d;
-  LinRange(double a_, double b_, int64_t n) : a((P)a_), b((P)b_), d(n - 1 > 1 ? n - 1 : 1) {}
+  int64_t d, off;
+  LinRange(double a_, double b_, int64_t n, int64_t off_ = 0) : a((P)a_), b((P)b_), d(n - 1 > 1 ? n - 1 : 1), off(off_) {}
   P operator[](int64_t i) const {
-    double t = (double)i / (double)d;
+    double t = (double)(i + off) / (double)d;
     double u = (1.0 - t) * (double)a;
     double v = t * (double)b;
     return (P)(u + v);
@@ -150,8 +153,8 @@ void mc_sweep(const T* sdf, int64_t nx, int64_t ny, int64_t nz, I iso, const Lin
 
 template <class T, class I, class P, class V>
 void run_mc(const T* sdf, int64_t nx, int64_t ny, int64_t nz, I iso, double x0, double x1, double y0,
-            double y1, double z0, double z1, int nthreads, int64_t xlo, int64_t xhi, Result& out) {
-  LinRange<P> xp(x0, x1, nx), yp(y0, y1, ny), zp(z0, z1, nz);
+            double y1, double z0, double z1, int nthreads, int64_t xlo, int64_t xhi, int64_t x_off, int64_t nx_glob, Result& out) {
+  LinRange<P> xp(x0, x1, nx_glob > 0 ? nx_glob : nx, x_off), yp(y0, y1, ny), zp(z0, z1, nz);
   std::vector<V>& vts = verts_of<V>(out);
   out.vert_is_f64 = std::is_same<V, double>::value;
   if (nx < 2 || ny < 2 || nz < 2) return;
@@ -337,6 +340,7 @@ struct Args {
   int range_kind;
   int nthreads;
   int64_t xlo, xhi;  // voxel x-plane range of the sweep, -1 = whole volume (bench samples)
+  int64_t x_off = 0, nx_glob = 0;  // MC only: the array is the slab [x_off, x_off + nx) of a volume with nx_glob samples along x
 };
 
 template <class T, class I, class E, class P>
@@ -347,9 +351,9 @@ void dispatch_v(const Args& a, Result& out) {
              (a.algo == 1 && std::is_same<E, double>::value);
   if (a.algo == 0) {
     if (f64)
-      run_mc<T, I, P, double>((const T*)a.sdf, a.nx, a.ny, a.nz, (I)a.iso, a.x0, a.x1, a.y0, a.y1, a.z0, a.z1, a.nthreads, a.xlo, a.xhi, out);
+      run_mc<T, I, P, double>((const T*)a.sdf, a.nx, a.ny, a.nz, (I)a.iso, a.x0, a.x1, a.y0, a.y1, a.z0, a.z1, a.nthreads, a.xlo, a.xhi, a.x_off, a.nx_glob, out);
     else
-      run_mc<T, I, P, float>((const T*)a.sdf, a.nx, a.ny, a.nz, (I)a.iso, a.x0, a.x1, a.y0, a.y1, a.z0, a.z1, a.nthreads, a.xlo, a.xhi, out);
+      run_mc<T, I, P, float>((const T*)a.sdf, a.nx, a.ny, a.nz, (I)a.iso, a.x0, a.x1, a.y0, a.y1, a.z0, a.z1, a.nthreads, a.xlo, a.xhi, a.x_off, a.nx_glob, out);
   } else {
     if (f64)
       run_mt<T, I, E, P, double>((const T*)a.sdf, a.nx, a.ny, a.nz, (I)a.iso, (E)a.eps, a.x0, a.x1, a.y0, a.y1, a.z0, a.z1, a.nthreads, a.xlo, a.xhi, out);
@@ -400,6 +404,19 @@ void* oracle_isosurface(int algo, const void* sdf, int sdf_is_f64, int64_t nx, i
                         int iso_is_f32, double eps, int eps_is_f32, double x0, double x1, double y0, double y1,
                         double z0, double z1, int range_kind, int nthreads, int64_t xlo, int64_t xhi) {
   Args a{algo, sdf, sdf_is_f64, nx, ny, nz, iso, iso_is_f32, eps, eps_is_f32, x0, x1, y0, y1, z0, z1, range_kind, nthreads, xlo, xhi};
+  Result* r = new Result();
+  if (sdf_is_f64) dispatch_i<double>(a, *r);
+  else dispatch_i<float>(a, *r);
+  return r;
+}
+// Marching Cubes on the slab of samples [x_offset, x_offset + nx) of a volume with nx_global samples along x: vertex
+// coordinates are those of the whole volume, face indices are relative to the slab's first vertex.
+void* oracle_isosurface_slab(int algo, const void* sdf, int sdf_is_f64, int64_t nx, int64_t ny, int64_t nz, double iso,
+                             int iso_is_f32, double eps, int eps_is_f32, double x0, double x1, double y0, double y1,
+                             double z0, double z1, int range_kind, int nthreads, int64_t x_offset, int64_t nx_global) {
+  if (algo != 0) return nullptr;  // MT shares vertices across voxels: no slab-wise restatement
+  Args a{algo, sdf, sdf_is_f64, nx, ny, nz, iso, iso_is_f32, eps, eps_is_f32, x0, x1, y0, y1, z0, z1, range_kind, nthreads, -1, -1};
+  a.x_off = x_offset, a.nx_glob = nx_global;
   Result* r = new Result();
   if (sdf_is_f64) dispatch_i<double>(a, *r);
   else dispatch_i<float>(a, *r);

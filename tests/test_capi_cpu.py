@@ -10,7 +10,7 @@ def test_library_exports_every_declared_symbol(pkg):
     assert "b200iso_count" in names and "b200iso_generate" in names and len(names) >= 14
     for n in names:
         assert hasattr(L, n), n
-    assert L.b200iso_version() >= 1000
+    assert L.b200iso_version() >= 2000
 
 
 def test_params_mirror_reference_call_forms(pkg):
@@ -28,6 +28,12 @@ def test_params_mirror_reference_call_forms(pkg):
     f = np.float32
     p = api.make_params(api.MarchingCubes(iso=f(0)), (f(-2), f(2)), (f(-2), f(2)), (f(-2), f(2)))
     assert p.range_kind == capi.RANGE_F32 and p.iso_is_f32 == 1
+    # mixed endpoint types: the vertex type follows eltype(first(X)) only (src/marching_cubes.jl:31), the coordinates
+    # follow LinRange(first(X), last(X), n), i.e. the promotion of BOTH endpoints (:36-38)
+    for rng, kind in (((0, 1.0), capi.RANGE_INT), ((0.0, 1), capi.RANGE_F64), ((f(0), 1.0), capi.RANGE_INT),
+                      ((0, f(1)), capi.RANGE_F32), ((f(0), 1), capi.RANGE_F32), ((0.0, f(1)), capi.RANGE_F64)):
+        p = api.make_params(api.MarchingCubes(iso=f(0)), rng, rng, rng)
+        assert p.range_kind == kind and (p.x0, p.x1) == (0.0, 1.0), rng
 
 
 def test_argument_errors(pkg):

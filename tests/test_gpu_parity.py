@@ -259,12 +259,10 @@ def test_tall_grids(pkg, oracle, algo, shape):
     _check(pkg, oracle, pkg.synth.noise(shape, seed=9), algo, iso=0.9)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("shape,kind", [((48, 40, 56), "gyroid"), ((33, 21, 300), "noise"), ((20, 130, 37), "sphere"), ((3, 3, 3), "noise"),
                                         ((300, 24, 70), "gyroid"), ((129, 9, 33), "noise"), ((515, 6, 40), "gyroid")])
-def test_fused_single_pass_extract(pkg, oracle, shape, kind, mode):
-    """b200iso_extract_async in both strategies: 0 = kernels back to back, 1 = fused count/scan/generate kernel
-    (decoupled look-back inside generate)."""
+def test_one_enqueue_extract(pkg, oracle, shape, kind):
+    """b200iso_extract_async: classify, count + scan and generate in one enqueue into buffers with a capacity."""
     import torch
     s = getattr(pkg.synth, kind)(shape)
     vo, fo = oracle.isosurface(s, 0, iso_is_f32=True)
@@ -276,7 +274,6 @@ def test_fused_single_pass_extract(pkg, oracle, shape, kind, mode):
     verts = torch.full((len(vo) + 3, 3), -7.0, dtype=torch.float32, device="cuda")
     faces = torch.full((len(fo) + 3, 3), -7, dtype=torch.int64, device="cuda")
     h.set_stream(torch.cuda.current_stream().cuda_stream)
-    h.set_extract_mode(mode)
     for _ in range(2):  # twice: the scan state must be reset between calls
         h.extract_async(p, t.data_ptr(), nx, ny, nz, nx, verts.data_ptr(), verts.shape[0], faces.data_ptr(), faces.shape[0], 0, 0,
                         totals.data_ptr())
@@ -300,7 +297,7 @@ def test_fused_single_pass_extract(pkg, oracle, shape, kind, mode):
     h.close()
 
 
-def test_fused_extract_mt_falls_back_to_two_kernels(pkg, oracle):
+def test_one_enqueue_extract_mt(pkg, oracle):
     import torch
     s = pkg.synth.gyroid((30, 31, 64))
     vo, fo = oracle.isosurface(s, 1, iso_is_f32=True, eps_is_f32=True)
@@ -348,18 +345,23 @@ def test_full_size_1024_gyroid_properties(pkg, oracle):
         assert torch.equal(sv, v[vo: vo + sv.shape[0]]) and torch.equal(sf, f[fo: fo + sf.shape[0]])
         vo += sv.shape[0]
         fo += sf.shape[0]
-    # (4) oracle on three thin x-ranges (with their halo plane), coordinates of the whole volume
-    for xa in (0, 517, n - 6):
-        xb = xa + 6
-        host = np.asfortranarray(t[xa:xb].cpu().numpy())
-        gv, gf = pkg.api.isosurface_slab(host, m, xa, n, 0)
-        # oracle: same slab as an independent volume whose X range is the slab's part of [-1, 1]
-        xs = -1.0 + 2.0 * np.arange(n) / (n - 1)
-        ov, of = oracle.isosurface(host, 0, iso_is_f32=True, ranges=((float(xs[xa]), float(xs[xb - 1])), (-1, 1), (-1, 1)),
-                                   range_kind=oracle.RANGE_F64)
-        assert np.array_equal(gf, of)
-        assert gv.shape == ov.shape and np.array_equal(gv[:, 1:], ov[:, 1:].astype(np.float32))
-        assert np.abs(gv[:, 0].astype(np.float64) - ov[:, 0]).max() < 1e-6  # x: slab-local vs global LinRange rounding
+    # (4) the oracle's sweep of three x-ranges of the SAME host field, compared bit for bit with the corresponding
+    # slices of the whole-volume result above -- i.e. with what the benchmarked kernels (TMA classify included) wrote
+    assert pkg.api.get_handle(0).classify_path() == pkg.capi.CLASSIFY_TMA
+    host = t.cpu().numpy()
+    assert host.flags.f_contiguous
+    vh, fh = v.cpu().numpy(), f.cpu().numpy()
+    for xlo in (0, 517, n - 7):
+        xhi = xlo + 6
+        ov, of = oracle.isosurface(host, 0, iso_is_f32=True, xrange=(xlo, xhi))
+        v0 = f0 = 0
+        if xlo > 0:  # vertices / faces of the voxel planes below the range
+            _, v0, f0, _ = pkg.api.slab_count(t[0:xlo + 1], m, 0, n)
+        assert len(ov) > 10000
+        assert np.array_equal(fh[f0:f0 + len(of)], of + v0), xlo
+        assert _bits_equal(vh[v0:v0 + len(ov)], ov), xlo
+        if xhi == n - 1:
+            assert v0 + len(ov) == len(vh) and f0 + len(of) == len(fh)
 
 
 # ---- Float64 fields: the reference's own test inputs run through the CUDA path unchanged ----
@@ -618,3 +620,150 @@ def test_c_example_runs_through_the_c_abi(pkg, c_example):
     r = subprocess.run([exe, "96"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "identical bytes" in r.stdout
+
+
+# ---- the TMA-staged classify kernel (what the 1024^3 benchmark times) against the oracle -------------------------
+TMA_SHAPES = [(16, 16, 16), (33, 20, 47), (5, 130, 37), (129, 7, 70), (12, 9, 260), (131, 9, 40), (260, 5, 1030), (2, 2, 2),
+              (127, 3, 33), (128, 4, 32), (256, 3, 513)]
+
+
+@pytest.fixture
+def tma_handle(pkg):
+    """The cached handle of device 0 with the classify kernel forced to the TMA path."""
+    h = pkg.api.get_handle(0)
+    h.set_classify_mode(1)
+    yield h
+    h.set_classify_mode(-1)
+
+
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+@pytest.mark.parametrize("shape", TMA_SHAPES)
+def test_tma_classify_parity_shapes(pkg, oracle, tma_handle, algo, shape):
+    """Ragged dimensions (nx not a multiple of 128, nz not a multiple of 8 / 32 / 512: NaN out-of-bounds fill of the
+    tensor map), every shape through signpack_tma_kernel, bit-exact against the oracle incl. the case indices."""
+    for s in (pkg.synth.gyroid(shape), pkg.synth.noise(shape, seed=17)):
+        _check(pkg, oracle, s, algo)
+        assert tma_handle.classify_path() == pkg.capi.CLASSIFY_TMA
+        c = pkg.api.case_indices(s, _method(pkg, algo, 0.0, True))
+        assert tma_handle.classify_path() == pkg.capi.CLASSIFY_TMA
+        assert np.array_equal(c, oracle.case_indices(s, ALGOS[algo], iso_is_f32=True))
+
+
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+def test_tma_classify_nan_inf_and_float64_iso(pkg, oracle, tma_handle, algo):
+    s = pkg.synth.gyroid((70, 50, 90)).copy(order="F")
+    s[3, 4, 5] = np.nan
+    s[69, 49, 89] = np.nan
+    s[7, 7, 7] = np.inf
+    s[2, 9, 4] = -np.inf
+    _check(pkg, oracle, s, algo)
+    assert tma_handle.classify_path() == pkg.capi.CLASSIFY_TMA
+    for iso, f32 in ((0.25, False), (1e-9, False), (-0.3, True)):
+        c = pkg.api.case_indices(s, _method(pkg, algo, iso, f32))
+        assert np.array_equal(c, oracle.case_indices(s, ALGOS[algo], iso=iso, iso_is_f32=f32))
+    assert tma_handle.classify_path() == pkg.capi.CLASSIFY_TMA
+
+
+def test_tma_classify_padded_device_rows(pkg, oracle, tma_handle):
+    """Device-resident field whose leading dimension is larger than nx (an x-slab view of a bigger array)."""
+    import torch
+    s = pkg.synth.gyroid((150, 40, 50))
+    store = torch.zeros((50, 40, 152), dtype=torch.float32, device="cuda")
+    store[:, :, :150] = torch.from_numpy(np.ascontiguousarray(s.transpose(2, 1, 0))).cuda()
+    for xa, xb in ((0, 150), (4, 137), (128, 150)):  # (16-byte aligned starts: the tensor map needs them)
+        t = store.permute(2, 1, 0)[xa:xb]
+        for algo in ("MC", "MT"):
+            v, f = pkg.isosurface(t, _method(pkg, algo, 0.0, True))
+            assert tma_handle.classify_path() == pkg.capi.CLASSIFY_TMA
+            vo, fo = oracle.isosurface(s[xa:xb], ALGOS[algo], iso_is_f32=True, eps_is_f32=True)
+            assert np.array_equal(f.cpu().numpy(), fo) and _bits_equal(v.cpu().numpy(), vo)
+    t = store.permute(2, 1, 0)[3:150]  # unaligned start: no tensor map, the scalar-load kernel takes over
+    v, f = pkg.isosurface(t, _method(pkg, "MC", 0.0, True))
+    assert tma_handle.classify_path() == pkg.capi.CLASSIFY_SCALAR
+    vo, fo = oracle.isosurface(s[3:150], 0, iso_is_f32=True)
+    assert np.array_equal(f.cpu().numpy(), fo) and _bits_equal(v.cpu().numpy(), vo)
+
+
+def test_tma_and_ldg_classify_give_the_same_bits_512(pkg, oracle):
+    """configs[1] through both classify kernels: identical meshes (the LDG one is pinned to the oracle above)."""
+    h = pkg.api.get_handle(0)
+    s = pkg.synth.gyroid(512)
+    m = pkg.MarchingCubes(iso=pkg.Float32(0))
+    out = {}
+    try:
+        for mode in (0, 1):
+            h.set_classify_mode(mode)
+            out[mode] = pkg.isosurface(s, m)
+            assert h.classify_path() == (pkg.capi.CLASSIFY_TMA if mode else pkg.capi.CLASSIFY_LDG128)
+    finally:
+        h.set_classify_mode(-1)
+    assert np.array_equal(out[0][1], out[1][1]) and _bits_equal(out[0][0], out[1][0])
+    vo, fo = oracle.isosurface(s, 0, iso_is_f32=True)
+    assert np.array_equal(out[1][1], fo) and _bits_equal(out[1][0], vo)
+
+
+# ---- BASELINE configs[4]: the multi-sphere/torus field ------------------------------------------------------------
+@pytest.mark.parametrize("algo", ["MC", "MT"])
+def test_parity_multisphere_torus_256(pkg, oracle, algo):
+    s = pkg.synth.multisphere_torus(256)
+    v, f = _check(pkg, oracle, s, algo)
+    assert len(f) > 50000
+
+
+@pytest.mark.parametrize("xa", [0, 700, 1021, 2042])
+def test_parity_multisphere_torus_2048_slabs(pkg, oracle, xa):
+    """configs[4] at its full 2048^3 size, slab-wise: Marching Cubes carries no state between voxels
+    (src/marching_cubes.jl:40-62), so six sample planes of the 2048^3 field with the whole volume's coordinates are
+    exactly that part of the whole sweep -- for the oracle (slab mode) and for the GPU (x_offset / nx_global)."""
+    n, w = 2048, 6
+    slab = pkg.synth.multisphere_torus((n, n, n), x_slice=(xa, xa + w))
+    assert slab.shape == (w, n, n)
+    m = pkg.MarchingCubes(iso=pkg.Float32(0))
+    gv, gf = pkg.api.isosurface_slab(slab, m, xa, n, 0)
+    assert pkg.api.get_handle(0).classify_path() == pkg.capi.CLASSIFY_TMA  # 8192 classify tasks: the automatic rule picks TMA
+    ov, of = oracle.isosurface(slab, 0, iso_is_f32=True, slab=(xa, n))
+    assert np.array_equal(gf, of) and _bits_equal(gv, ov)
+    if xa == 1021:
+        assert len(of) > 1000  # the torus crosses the middle of the volume
+
+
+# ---- SURVEY 8(f)-2: Marching Tetrahedra at 1024^3 -----------------------------------------------------------------
+def test_full_size_1024_gyroid_mt_against_oracle_ranges(pkg, oracle):
+    """MT on the 1024^3 gyroid: totals, manifold-style invariants, and the oracle's sweep of x-ranges compared with the
+    corresponding slices of the whole-volume result.  MT shares vertices between voxels, so the oracle sweeps the range
+    plus one voxel plane below it (which creates the shared vertices first); vertex ids then differ by a constant for
+    vertices created inside the range, and every face must have bit-identical corner coordinates."""
+    import torch
+    n = 1024
+    t = pkg.synth.gyroid_torch(n, "cuda")
+    m = pkg.MarchingTetrahedra(iso=pkg.Float32(0), eps=pkg.Float32(1e-3))
+    v, f = pkg.isosurface(t, m)
+    assert v.dtype == torch.float32 and int(f.min()) == 1 and int(f.max()) == v.shape[0]
+    assert bool(torch.isfinite(v).all())
+    # MT vertex count identity (SURVEY.md Appendix C): one vertex per sign-changing lattice edge of the 7 direction types
+    b = t < 0
+    nv_expect = 0
+    for dx, dy, dz in ((1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (1, 0, 1), (0, 1, 1), (1, 1, 1)):
+        nv_expect += int((b[: n - dx, : n - dy, : n - dz] != b[dx:, dy:, dz:]).sum())
+    assert v.shape[0] == nv_expect
+    host = t.cpu().numpy()
+    vh, fh = v.cpu().numpy(), f.cpu().numpy()
+    del v, f, b
+    for xlo in (1, 600, n - 4):
+        xhi = xlo + 3
+        # totals of the voxel planes [0, xlo) and [0, xlo - 1): where the range and its ghost plane start in the output
+        _, v_lo, f_lo, _ = pkg.api.slab_count(t[0:xlo + 1], m, 0, n)
+        ov, of = oracle.isosurface(host, 1, iso_is_f32=True, eps_is_f32=True, xrange=(xlo - 1, xhi))
+        gv, gf = oracle.isosurface(host, 1, iso_is_f32=True, eps_is_f32=True, xrange=(xlo - 1, xlo), copy=False)  # ghost plane alone
+        of_r = of[gf:]  # faces of the range proper
+        fg = fh[f_lo:f_lo + len(of_r)]
+        assert len(of_r) > 10000
+        # bit-identical corner coordinates, face by face
+        assert _bits_equal(vh[fg - 1], ov[of_r - 1]), xlo
+        # vertices created inside the range: ids differ from the oracle's by one constant
+        own = of_r > gv
+        d = fg[own] - of_r[own]
+        assert d.size > 0 and int(d.min()) == int(d.max()) == v_lo - gv, xlo
+        # vertices of the ghost plane keep their relative order
+        gh = ~own
+        assert np.array_equal(np.argsort(fg[gh], kind="stable"), np.argsort(of_r[gh], kind="stable"))

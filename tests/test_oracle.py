@@ -206,3 +206,21 @@ def test_mt_sphere_is_a_closed_manifold(oracle, pkg):
     directed = {(int(a), int(b)) for a, b in e}
     assert len(directed) == len(e) and all((b, a) in directed for a, b in directed)
     assert len(v) - len(und) + len(f) == 2  # Euler characteristic of a sphere
+
+
+def test_slab_mode_equals_the_x_range_of_the_whole_sweep(oracle):
+    """oracle.isosurface(slab=...) (used for the slab-wise parity of the 2048^3 config) is bit-identical to the
+    corresponding x-range of the whole-volume sweep: Marching Cubes carries no state between voxels."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from __graft_entry__ import load_package
+    synth = load_package().synth
+    s = synth.gyroid((40, 21, 30))
+    rr = ((0.0, 3.0), (-1.0, 1.0), (2.0, 5.0))
+    for rk in (oracle.RANGE_INT, oracle.RANGE_F32, oracle.RANGE_F64):
+        for xa, xb in ((0, 9), (10, 26), (33, 40)):
+            vs, fs = oracle.isosurface(s[xa:xb], oracle.MC, iso=0.05, iso_is_f32=True, ranges=rr, range_kind=rk, slab=(xa, 40))
+            vr, fr = oracle.isosurface(s, oracle.MC, iso=0.05, iso_is_f32=True, ranges=rr, range_kind=rk, xrange=(xa, xb - 1))
+            assert len(vs) > 0 and np.array_equal(fs, fr)
+            assert np.array_equal(vs.view(np.uint32 if vs.dtype == np.float32 else np.uint64),
+                                  vr.view(np.uint32 if vr.dtype == np.float32 else np.uint64))

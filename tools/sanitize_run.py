@@ -13,6 +13,16 @@ for s in (pkg.synth.gyroid((48, 40, 56)), pkg.synth.noise((33, 21, 300), seed=1)
         v, f = pkg.isosurface(s, m)
         c = pkg.api.case_indices(s, m)
         print(s.shape, s.dtype, type(m).__name__, len(v), len(f), int(c.sum()))
+# the TMA-staged classify kernel on ragged shapes (NaN out-of-bounds fill)
+_h = pkg.api.get_handle(0)
+_h.set_classify_mode(1)
+for shp in ((131, 9, 40), (33, 20, 47), (260, 5, 1030)):
+    s = pkg.synth.gyroid(shp)
+    for m in (pkg.MarchingCubes(iso=F(0)), pkg.MarchingTetrahedra(iso=F(0), eps=F(1e-3))):
+        v, f = pkg.isosurface(s, m)
+        assert _h.classify_path() == pkg.capi.CLASSIFY_TMA
+        print("tma", shp, type(m).__name__, len(v), len(f))
+_h.set_classify_mode(-1)
 s = pkg.synth.gyroid((41, 19, 70))
 for m in (pkg.MarchingCubes(iso=F(0)), pkg.MarchingTetrahedra(iso=F(0), eps=F(1e-3))):
     gh = isinstance(m, pkg.MarchingTetrahedra)

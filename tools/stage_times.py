@@ -7,12 +7,11 @@ from __graft_entry__ import load_package
 pkg = load_package()
 algo = sys.argv[1] if len(sys.argv) > 1 else "MC"
 f64 = "f64" in sys.argv  # Float64 field (and therefore Float64 vertices)
-fused = any(a.startswith("mode") for a in sys.argv)
-mode = int([a for a in sys.argv if a.startswith("mode")][0][4:]) if fused else 0
+fused = "oneq" in sys.argv  # time b200iso_extract_async (one enqueue) end to end as well
+mode = 0
 sizes = [int(a) for a in sys.argv[2:] if a.isdigit()] or [256, 512, 1024]
 h = pkg.capi.Handle(0)
 h.enable_timing(True)
-h.set_extract_mode(mode)
 for n in sizes:
     t = pkg.synth.gyroid_torch(n, "cuda")
     if f64:
@@ -45,6 +44,6 @@ for n in sizes:
         h.use_own_stream()
     esz = 8 if f64 else 4
     B = esz * n ** 3 + 3 * esz * nv + 24 * nf
-    print(f"{algo}{" mode%d" % mode if fused else ""} n={n} nv={nv} nf={nf} classify={tm['classify_ms']:.3f} count={tm['count_scan_ms']:.3f} gen={tm['generate_ms']:.3f} "
+    print(f"{algo}{" oneq" if fused else ""} n={n} nv={nv} nf={nf} classify={tm['classify_ms']:.3f} count={tm['count_scan_ms']:.3f} gen={tm['generate_ms']:.3f} "
           f"total={tot:.3f} ms  {(n-1)**3/tot/1e6:.1f} Gvox/s  {B/tot/1e6:.0f} GB/s  classify {esz*n**3/tm['classify_ms']/1e6:.0f} GB/s", flush=True)
     del t, verts, faces
