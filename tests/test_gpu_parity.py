@@ -324,6 +324,7 @@ def test_full_size_1024_gyroid_properties(pkg, oracle):
     t = pkg.synth.gyroid_torch(n, "cuda")
     m = pkg.MarchingCubes(iso=pkg.Float32(0))
     v, f = pkg.isosurface(t, m)
+    assert pkg.api.get_handle(0).classify_path() == pkg.capi.CLASSIFY_TMA  # the kernel the benchmark times
     assert v.shape == (40573677, 3) and f.shape == (20286967, 3) and v.dtype == torch.float32
     assert int(f.min()) == 1 and int(f.max()) == v.shape[0]
     assert bool(torch.isfinite(v).all()) and float(v.min()) >= -1.0 and float(v.max()) <= 1.0
@@ -347,7 +348,6 @@ def test_full_size_1024_gyroid_properties(pkg, oracle):
         fo += sf.shape[0]
     # (4) the oracle's sweep of three x-ranges of the SAME host field, compared bit for bit with the corresponding
     # slices of the whole-volume result above -- i.e. with what the benchmarked kernels (TMA classify included) wrote
-    assert pkg.api.get_handle(0).classify_path() == pkg.capi.CLASSIFY_TMA
     host = t.cpu().numpy()
     assert host.flags.f_contiguous
     vh, fh = v.cpu().numpy(), f.cpu().numpy()
