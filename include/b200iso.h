@@ -96,6 +96,13 @@ int b200iso_use_own_stream(b200iso_handle* h);
 enum { B200ISO_CLASSIFY_LDG128 = 0, B200ISO_CLASSIFY_TMA = 1, B200ISO_CLASSIFY_SCALAR = 2, B200ISO_CLASSIFY_F64 = 3 };
 int b200iso_set_classify_mode(b200iso_handle* h, int mode);
 int b200iso_classify_path(b200iso_handle* h);
+/* Marching Cubes on the TMA classify path: every classify CTA carries `warps` extra warps that count the generate
+ * blocks from the finished rows of the bit-field while the field still streams (the classify kernel is bound by HBM
+ * and leaves most issue slots idle); the count kernel behind it only takes what they did not get to.  0 switches
+ * this off (count kernel only), default 4, at most 8; results are identical.  Environment: B200ISO_RIDE=<warps>.
+ * b200iso_ride_claimed: how many generate blocks the riding warps counted in the last count (synchronises). */
+int b200iso_set_ride_warps(b200iso_handle* h, int warps);
+int64_t b200iso_ride_claimed(b200iso_handle* h);
 
 /* ---- the drop-in pair: replaces the body of isosurface(sdf, method, X, Y, Z) ---------------------------
  * b200iso_count   : classify + count + scan.  `sdf` is Float32 (Float64 if p->field_is_f64), host or device (mem), nx*ny*nz samples with

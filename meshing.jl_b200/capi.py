@@ -81,6 +81,9 @@ def load():
     L.b200iso_add_vertex_base_async.argtypes = [vp, vp, i64, vp, vp]
     L.b200iso_set_classify_mode.argtypes = [vp, ci]
     L.b200iso_classify_path.argtypes = [vp]
+    L.b200iso_set_ride_warps.argtypes = [vp, ci]
+    L.b200iso_ride_claimed.argtypes = [vp]
+    L.b200iso_ride_claimed.restype = i64
     L.b200iso_set_peer_timeout.argtypes = [vp, ctypes.c_double]
     L.b200iso_case_indices.argtypes = [vp, vp, ci]
     L.b200iso_enable_timing.argtypes = [vp, ci]
@@ -177,6 +180,14 @@ class Handle:
     def classify_path(self):
         """CLASSIFY_* of the last count (-1 before the first)"""
         return self.L.b200iso_classify_path(self.h)
+
+    def set_ride_warps(self, warps):
+        """counting warps per TMA classify CTA (0 = count kernel only)"""
+        _check(self.L.b200iso_set_ride_warps(self.h, int(warps)))
+
+    def ride_claimed(self):
+        """generate blocks counted inside the classify kernel in the last count"""
+        return self.L.b200iso_ride_claimed(self.h)
 
     def set_peer_timeout(self, seconds):
         """how long exchange_async waits for its peers; <= 0 waits for ever"""

@@ -103,6 +103,12 @@ struct b200iso_handle {
   DevBuf<unsigned long long> woff;    // MC: exclusive (vertex, face) prefix of every generate block; MT: raw block totals
   DevBuf<double> coords;
   DevBuf<uint8_t> cases;             // b200iso_case_indices(HOST): device scratch, kept across calls
+  // counting warps inside the TMA classify kernel (signpack_tma.cuh): header | next_x[nbi] | rows_done[ny]
+  DevBuf<unsigned int> ride;
+  long long ride_ny = -1, ride_tpr = -1, ride_nbi = -1;  // shape the cumulative row counters belong to
+  unsigned int ride_step = 0;
+  int ride_stop = iso::TM_WARPS * iso::SP_ZW * 3 / 4;  // counting warps stop claiming at 3/4 of the CTA's classify work (env B200ISO_RIDE_STOP: z-words of 64)
+  int ride_warps = 6;  // counting warps per TMA classify CTA (0 = separate count kernel only; b200iso_set_ride_warps, env B200ISO_RIDE)
   // grid coordinates are a function of the call's shape and ranges only: recomputed when those change
   struct CoordsKey {
     long long nx = -1, ny = -1, nz = -1, xoff = 0, nxg = 0;
@@ -224,6 +230,7 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
   if (!step_begun) h->begin_step();
   if (int rc = h->rec(b200iso_handle::E_C0)) return rc;
   // (1) sign-pack; its block 0 also clears the scan state (ticket + chain) -- no memset nodes in the step
+  bool ride = false;  // the classify kernel counted (most of) the generate blocks itself
   {
     const bool f64 = p->field_is_f64 != 0;
     const bool vec = !f64 && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(sdf_dev) & 15) == 0);
@@ -237,9 +244,28 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
     // (measured: TMA wins on big fields -- 0.656 vs 0.694 ms at 1024^3 -- and loses a few % when the grid is under two waves)
     const bool tma_wanted = h->tma_mode == 1 || (h->tma_mode < 0 && ntasks >= 4096);
     if (vec && tma_wanted && iso::make_field_tmap(&tmap, sdf_f, nx, ny, nz, ldx)) {
-      // TMA-staged classify: same tasks, cp.async.bulk.tensor boxes + per-warp mbarrier pipeline
+      // TMA-staged classify: same tasks, cp.async.bulk.tensor boxes + per-warp mbarrier pipeline; for Marching Cubes
+      // its CTAs carry counting warps that count the generate blocks while the field streams (signpack_tma.cuh)
+      iso::CountRide cr{};
+      cr.g = g;
+      if (!mt && h->ride_warps > 0) {
+        const long long tpr = (long long)nxseg * nzc, nbi = g.blocks_per_row;
+        const size_t words = (size_t)iso::RIDE_HDR + (size_t)nbi + (size_t)ny;
+        if (int rc = h->ride.reserve(words)) return rc;
+        if (h->ride_ny != ny || h->ride_tpr != tpr || h->ride_nbi != nbi ||
+            (unsigned long long)(h->ride_step + 2) * (unsigned long long)tpr >= (1ull << 31)) {
+          CU(cudaMemsetAsync(h->ride.p, 0, words * sizeof(unsigned int), st));
+          h->ride_ny = ny, h->ride_tpr = tpr, h->ride_nbi = nbi, h->ride_step = 0;
+        }
+        cr.nbi = (int)nbi, cr.woff = h->woff.p, cr.head = h->ride.p, cr.next_x = h->ride.p + iso::RIDE_HDR;
+        cr.rows_done = cr.next_x + nbi;
+        cr.target = ++h->ride_step * (unsigned int)tpr;
+        cr.stop_at = h->ride_stop;
+        ride = true;
+      }
       const unsigned tb = (unsigned)((ntasks + iso::TM_WARPS - 1) / iso::TM_WARPS);
-      iso::signpack_tma_kernel<<<tb, iso::TM_WARPS * 32, iso::TM_SMEM, st>>>(tmap, h->bits.p, g.nx, g.ny, g.nz, g.W, thr, nxseg, ntasks, h->chain.p, nclear);
+      iso::signpack_tma_kernel<<<tb, (iso::TM_WARPS + (ride ? h->ride_warps : 0)) * 32, iso::TM_SMEM, st>>>(tmap, h->bits.p, g.nx, g.ny, g.nz, g.W, thr, nxseg, nzc,
+                                                                                                  ntasks, h->chain.p, nclear, cr);
       h->classify_path = B200ISO_CLASSIFY_TMA;
     } else if (vec) {
       iso::signpack_kernel<true, float><<<nb, iso::SP_WARPS * 32, 0, st>>>(sdf_f, h->bits.p, g.nx, g.ny, g.nz, g.ldx, g.W, thr, nxseg, ntasks, h->chain.p, nclear);
@@ -261,9 +287,11 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
   h->totals_out = totals_out;
   if (!mt) {
     const unsigned ncb = (unsigned)((h->nblocks + iso::WC_THREADS / 32 - 1) / (iso::WC_THREADS / 32));
-    iso::mc_count_chunks_kernel<<<ncb, iso::WC_THREADS, 0, st>>>(h->bits.p, g, h->nblocks, h->woff.p);
+    // (after a classify with counting warps only the items they did not claim are left: blocks beyond them exit at once)
+    iso::mc_count_chunks_kernel<<<ncb, iso::WC_THREADS, 0, st>>>(h->bits.p, g, h->nblocks, h->woff.p, ride ? h->ride.p + iso::RIDE_HDR : nullptr);
     CU(cudaGetLastError());
-    iso::mc_scan_chunks_kernel<<<(unsigned)nsb, iso::SC_THREADS, 0, st>>>(h->woff.p, h->nblocks, chain, ticket, nsb, h->totals_dev, totals_out);
+    iso::mc_scan_chunks_kernel<<<(unsigned)nsb, iso::SC_THREADS, 0, st>>>(h->woff.p, h->nblocks, chain, ticket, nsb, h->totals_dev, totals_out,
+                                                                          ride ? h->ride.p : nullptr, ride ? iso::RIDE_HDR + g.blocks_per_row : 0);
   } else {
     iso::mt_count_kernel<<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->celloff.p, h->woff.p);
     CU(cudaGetLastError());
@@ -349,6 +377,8 @@ const char* b200iso_last_error(void) { return g_err; }
 
 static int create_impl(b200iso_handle* h) {
   if (const char* e = getenv("B200ISO_TMA")) h->tma_mode = atoi(e) != 0 ? 1 : 0;
+  if (const char* e = getenv("B200ISO_RIDE_STOP")) h->ride_stop = atoi(e);
+  if (const char* e = getenv("B200ISO_RIDE")) h->ride_warps = std::max(0, std::min(iso::TM_CNT_WARPS_MAX, atoi(e)));
   // per device: the TMA classify kernel needs more than the default 48 KB of dynamic shared memory
   CU(cudaFuncSetAttribute(iso::signpack_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iso::TM_SMEM));
   CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -386,7 +416,7 @@ int b200iso_destroy(b200iso_handle* h) {
   for (cudaEvent_t e : h->slab_ev) cudaEventDestroy(e);
   h->pool.release();
   h->bits.release(), h->celloff.release(), h->woff.release(), h->chain.release(), h->status.release(), h->coords.release(), h->field.release(), h->vstage.release(), h->fstage.release();
-  h->cases.release();
+  h->cases.release(), h->ride.release();
   if (h->totals_dev) cudaFree(h->totals_dev);
   if (h->totals_host) cudaFreeHost(h->totals_host);
   if (h->ev) {
@@ -421,6 +451,23 @@ int b200iso_set_classify_mode(b200iso_handle* h, int mode) {
 }
 
 int b200iso_classify_path(b200iso_handle* h) { return h ? h->classify_path : -1; }
+
+int b200iso_set_ride_warps(b200iso_handle* h, int warps) {
+  if (!h || warps < 0 || warps > iso::TM_CNT_WARPS_MAX) return fail(B200ISO_EINVAL, "bad handle or warp count (0..%d)", iso::TM_CNT_WARPS_MAX);
+  h->ride_warps = warps;
+  return 0;
+}
+
+int64_t b200iso_ride_claimed(b200iso_handle* h) {
+  if (!h || !h->ride.p) return 0;
+  DeviceGuard guard(h->device);
+  unsigned int v = 0;
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaMemcpy(&v, h->ride.p + 2, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return (int64_t)v;
+}
 
 int b200iso_set_peer_timeout(b200iso_handle* h, double seconds) {
   if (!h) return fail(B200ISO_EINVAL, "handle is NULL");

@@ -87,41 +87,36 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 }
 
 // (launch bound 6 blocks/SM = 40 registers, 75 % occupancy: 0.171 ms against 0.174 at 5 and 0.179 at 4 blocks/SM)
+// next_x: the counting warps inside the TMA classify kernel (signpack_tma.cuh) have already counted, of every y-block
+// bi, the generate blocks x < next_x[bi]; this kernel takes the rest (everything when next_x == nullptr).
 __global__ void __launch_bounds__(WC_THREADS, 6)
-mc_count_chunks_kernel(const uint32_t* __restrict__ bits, Grid g, long long nchunks, unsigned long long* __restrict__ woff) {
+mc_count_chunks_kernel(const uint32_t* __restrict__ bits, Grid g, long long nchunks, unsigned long long* __restrict__ woff,
+                       const unsigned int* __restrict__ next_x) {
   __shared__ uint8_t nf_s[256];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // items are numbered y-block-major: item = bi * nxv + x
+  const long long item0 = (long long)blockIdx.x * (WC_THREADS / 32);
+  const long long nxv = g.nx - 1;
+  if (next_x) {  // all of this block's items already counted?  (uniform over the block)
+    const long long last = min(item0 + WC_THREADS / 32, nchunks) - 1;
+    const long long b0 = item0 / nxv, b1 = last / nxv;
+    bool todo = false;
+    for (long long bi = b0; bi <= b1; ++bi) {
+      const long long xa = bi == b0 ? item0 - b0 * nxv : 0, xb = bi == b1 ? last - b1 * nxv : nxv - 1;  // x range of the block in bi
+      todo = todo || (long long)__ldg(next_x + bi) <= xb;
+      (void)xa;
+    }
+    if (!todo) return;
+  }
   nf_s[threadIdx.x] = (uint8_t)((ISO_MC_VERTS[threadIdx.x] >> 52) & 7);
   __syncthreads();
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long chunk = (long long)blockIdx.x * (WC_THREADS / 32) + w;
-  if (chunk >= nchunks) return;
-  uint32_t nv = 0, nf = 0;
-  const int x = (int)(chunk / g.blocks_per_row);
-  const int q_lo = (int)(chunk - (long long)x * g.blocks_per_row) * CB_THREADS;
-  for (int q0 = q_lo; q0 < q_lo + CB_THREADS && q0 < g.quads_per_row; q0 += 32) {
-    const int qr = q0 + lane;
-    const int y = (int)fast_div((unsigned)qr, g.wq_mul, g.wq_sh), zq = qr - y * g.Wq;
-    Quad q;
-    if (qr < g.quads_per_row && load_quad(bits, g, x, y, zq, q)) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint32_t mm = active_mask(q, i);
-        if (mm) {
-          nv += mc_nverts_masked(q, i, q.vm[i]);
-          while (mm) {
-            const int k = __ffs(mm) - 1;
-            mm &= mm - 1;
-            nf += nf_s[case_of<0>(q, i, k)];
-          }
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    nv += __shfl_xor_sync(0xffffffffu, nv, o);
-    nf += __shfl_xor_sync(0xffffffffu, nf, o);
-  }
+  const long long item = item0 + w;
+  if (item >= nchunks) return;
+  const long long bi = item / nxv, x = item - bi * nxv;
+  if (next_x && x < (long long)__ldg(next_x + bi)) return;  // counted inside the classify kernel
+  const long long chunk = x * g.blocks_per_row + bi;
+  uint32_t nv, nf;
+  mc_count_chunk<false>(bits, g, chunk, nf_s, nv, nf);
   if (lane == 0) woff[2 * chunk] = nv, woff[2 * chunk + 1] = nf;
 }
 
@@ -130,10 +125,18 @@ constexpr int SC_THREADS = 256, SC_PER = 4;  // scan block: 1024 (vertex, face) 
 // scan blocks (ticketed), totals from the last block.
 __global__ void __launch_bounds__(SC_THREADS)
 mc_scan_chunks_kernel(unsigned long long* __restrict__ woff, long long nchunks, unsigned long long* status, unsigned int* ticket,
-                      long long nsb, long long* totals_a, long long* totals_b) {
+                      long long nsb, long long* totals_a, long long* totals_b, unsigned int* ride, int nride) {
   __shared__ unsigned long long wsum_v[SC_THREADS / 32], wsum_f[SC_THREADS / 32];
   __shared__ unsigned long long base_s[2];
   __shared__ unsigned sb;
+  // the queues of the counting warps (cur_bi, next_x[]) are empty again for the next step: everything that reads them
+  // ran before this kernel.  ride[1] (statistics: blocks counted inside classify) moves to ride[2] first.
+  if (ride && blockIdx.x == 0) {
+    if (threadIdx.x == 0) ride[2] = ride[1];
+    __syncthreads();
+    for (int i = threadIdx.x; i < nride; i += SC_THREADS)
+      if (i != 2) ride[i] = 0u;
+  }
   if (threadIdx.x == 0) sb = atomicAdd(ticket, 1u);
   __syncthreads();
   const long long b = sb;

@@ -262,16 +262,28 @@ __device__ __forceinline__ void shift_up(const uint4 a, uint32_t nxt, uint32_t* 
 // Loads the quad-cell (x, y, zq) from the bit-field.  Returns false -- without building the shifted words --
 // when no sign changes anywhere in its 4x(128+1) samples (cheap test on the raw words): then no voxel of
 // the quad-cell is active.
+// CG = true: loads that bypass L1 (ld.global.cg).  The counting warps that run INSIDE the classify kernel read
+// bit-field rows other CTAs of the same launch have just written; L1 is not coherent and a 128-byte line can hold
+// words of a row that is not complete yet, so those reads must come from L2.
+template <bool CG>
+__device__ __forceinline__ uint4 ld_bits4(const uint32_t* p) {
+  return CG ? __ldcg(reinterpret_cast<const uint4*>(p)) : __ldg(reinterpret_cast<const uint4*>(p));
+}
+template <bool CG>
+__device__ __forceinline__ uint32_t ld_bits1(const uint32_t* p) {
+  return CG ? __ldcg(p) : __ldg(p);
+}
+template <bool CG = false>
 __device__ __forceinline__ bool load_quad(const uint32_t* __restrict__ bits, const Grid& g, int x, int y, int zq, Quad& q) {
   const uint32_t* c00 = bits + (long long)x * g.row_words + (long long)y * g.W + zq * 4;
   const uint32_t* c10 = c00 + g.row_words;
   const bool more = zq + 1 < g.Wq;
-  const uint4 a00 = __ldg(reinterpret_cast<const uint4*>(c00));
-  const uint4 a01 = __ldg(reinterpret_cast<const uint4*>(c00 + g.W));
-  const uint4 a10 = __ldg(reinterpret_cast<const uint4*>(c10));
-  const uint4 a11 = __ldg(reinterpret_cast<const uint4*>(c10 + g.W));
-  const uint32_t n00 = more ? __ldg(c00 + 4) : 0u, n01 = more ? __ldg(c00 + g.W + 4) : 0u;
-  const uint32_t n10 = more ? __ldg(c10 + 4) : 0u, n11 = more ? __ldg(c10 + g.W + 4) : 0u;
+  const uint4 a00 = ld_bits4<CG>(c00);
+  const uint4 a01 = ld_bits4<CG>(c00 + g.W);
+  const uint4 a10 = ld_bits4<CG>(c10);
+  const uint4 a11 = ld_bits4<CG>(c10 + g.W);
+  const uint32_t n00 = more ? ld_bits1<CG>(c00 + 4) : 0u, n01 = more ? ld_bits1<CG>(c00 + g.W + 4) : 0u;
+  const uint32_t n10 = more ? ld_bits1<CG>(c10 + 4) : 0u, n11 = more ? ld_bits1<CG>(c10 + g.W + 4) : 0u;
   // bits of samples beyond nz are 0, so an all-ones run that reaches the padding reads as "mixed" here;
   // that only costs the slow path, the exact valid-mask is applied below.
   const uint32_t nany = (n00 | n01 | n10 | n11) & 1u;
@@ -322,6 +334,43 @@ __device__ __forceinline__ uint32_t mc_nverts_masked(const Quad& q, int i, uint3
   return n;
 }
 
+
+// Marching Cubes count of one generate block ("chunk": CB_THREADS consecutive quad-cells of one voxel x-row), by ONE
+// warp: lane <-> quad-cell, 32 at a time.  vertices = crossed cube edges (12 masked popcounts per word), faces = table
+// look-up per active voxel (nf_s: 256-byte table in shared memory).  Returns the chunk's totals in every lane.
+template <bool CG>
+__device__ __forceinline__ void mc_count_chunk(const uint32_t* __restrict__ bits, const Grid& g, long long chunk, const uint8_t* nf_s,
+                                               uint32_t& nv_out, uint32_t& nf_out) {
+  const int lane = threadIdx.x & 31;
+  uint32_t nv = 0, nf = 0;
+  const int x = (int)(chunk / g.blocks_per_row);
+  const int q_lo = (int)(chunk - (long long)x * g.blocks_per_row) * CB_THREADS;
+  for (int q0 = q_lo; q0 < q_lo + CB_THREADS && q0 < g.quads_per_row; q0 += 32) {
+    const int qr = q0 + lane;
+    const int y = (int)fast_div((unsigned)qr, g.wq_mul, g.wq_sh), zq = qr - y * g.Wq;
+    Quad q;
+    if (qr < g.quads_per_row && load_quad<CG>(bits, g, x, y, zq, q)) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t mm = active_mask(q, i);
+        if (mm) {
+          nv += mc_nverts_masked(q, i, q.vm[i]);
+          while (mm) {
+            const int k = __ffs(mm) - 1;
+            mm &= mm - 1;
+            nf += nf_s[case_of<0>(q, i, k)];
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nv += __shfl_xor_sync(0xffffffffu, nv, o);
+    nf += __shfl_xor_sync(0xffffffffu, nf, o);
+  }
+  nv_out = nv, nf_out = nf;
+}
 
 // ---- block scans (256 threads) ---------------------------------------------------------------------------
 // exclusive scan in thread order; s_w: 8 words of shared scratch.  Contains two barriers.
@@ -680,13 +729,10 @@ __device__ __forceinline__ void store3(S* base, long long gi, S v0, S v1, S v2, 
     struct alignas(2 * sizeof(S)) S2 {
       S a, b;
     };
-    if ((gi & 1) == 0) {
-      *reinterpret_cast<S2*>(o) = S2{v0, v1};
-      o[2] = v2;
-    } else {
-      o[0] = v0;
-      *reinterpret_cast<S2*>(o + 1) = S2{v1, v2};
-    }
+    // (selects, not branches: even and odd elements of a warp issue the same two store instructions)
+    const bool odd = (gi & 1) != 0;
+    *reinterpret_cast<S2*>(o + (odd ? 1 : 0)) = S2{odd ? v1 : v0, odd ? v2 : v1};
+    o[odd ? 0 : 2] = odd ? v0 : v2;
   } else {
     o[0] = v0, o[1] = v1, o[2] = v2;
   }

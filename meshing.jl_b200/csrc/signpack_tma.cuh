@@ -59,24 +59,130 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
-__global__ void __launch_bounds__(TM_WARPS * 32)
+// ---- counting warps riding along in the classify CTAs ------------------------------------------------------
+// The classify warps are bound by HBM and leave three quarters of the SM's issue slots idle; the Marching Cubes count
+// (0.17 ms as a kernel of its own at 1024^3: issue-bound, reads only the bit-field) fits in them.  Every classify
+// CTA therefore carries a few extra warps that count generate blocks as soon as the bit-field rows they need are
+// complete.  The generate blocks of one "y-block" bi (block-in-row index: the same rows for every x) form one queue:
+//   - classify tasks are numbered y-major (all x-segments and z-chunks of row y, then row y + 1, ...), so rows
+//     complete in order while the kernel runs; a finished task bumps rows_done[y] (release);
+//   - a counting warp reads the current y-block (cur_bi), checks rows_done[] of its rows against the step's target
+//     (acquire), takes the next TM_CNT_BATCH values of x with ONE fetch-add on that y-block's counter (a
+//     compare-and-swap on a single queue head makes a thousand warps fight for the same item: measured 300 claims
+//     per step) and counts them from L2 (ld.global.cg: L1 is not coherent); an exhausted y-block advances cur_bi;
+//   - counting warps poll only while their CTA's classify warps still stream and leave with them (after the batch
+//     in hand), so they hold the CTA's shared memory against the next classify CTA only for that long.
+// Whatever is left when the kernel ends (the y-blocks of the last rows) is counted by mc_count_chunks_kernel, which
+// skips x < next_x[bi] -- the result never depends on how much was claimed here.
+// rows_done[] counts cumulatively over the steps (target = step number x tasks per row): no reset between steps;
+// cur_bi, next_x[] and the statistics word are zeroed by the scan kernel at the end of the step.
+constexpr int TM_CNT_WARPS_MAX = 8;  // counting warps per CTA: a launch parameter (blockDim), 4 by default
+constexpr unsigned TM_CNT_BATCH = 1;  // generate blocks per claim (more per claim = longer overhang past the classify warps)
+// layout of the ride buffer (unsigned int): [0] cur_bi, [1] claimed (statistics), [32 .. 32 + nbi) next_x, then rows_done[ny]
+constexpr int RIDE_HDR = 32;
+struct CountRide {
+  Grid g;                      // geometry of the count (same as generate)
+  int nbi;                     // y-blocks = generate blocks per voxel x-row; 0 = no counting warps
+  unsigned long long* woff;    // raw (vertex, face) pair per generate block
+  unsigned int* head;          // [0] cur_bi, [1] claimed
+  unsigned int* next_x;        // [nbi]
+  unsigned int* rows_done;     // [ny] finished classify tasks per sample row, cumulative over steps
+  unsigned int target;         // rows_done[y] >= target  <=>  row y is complete in this step
+  int stop_at;                 // counting warps stop claiming once the CTA's classify warps have finished this many z-words
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// cta_prog: z-words finished by the CTA's classify warps (SP_ZW per warp).  A counting warp that is still counting
+// when they are through keeps the CTA -- and its 96 KB of shared memory -- from the next classify CTA (measured:
+// classify 0.66 -> 0.72 ms with unbounded claiming), so claiming stops when the classify warps near their end.
+__device__ __forceinline__ void count_ride(const uint32_t* __restrict__ bits, const CountRide& cr, const volatile int* cta_prog,
+                                           const uint8_t* nf_s) {
+  const int lane = threadIdx.x & 31;
+  const Grid& g = cr.g;
+  const unsigned nxv = (unsigned)(g.nx - 1);
+  unsigned ready_bi = 0xffffffffu;  // y-block this warp has already seen complete
+  while (true) {
+    if (*cta_prog >= cr.stop_at) return;  // this CTA's classify warps are nearly through: leave the rest to later CTAs
+    unsigned int bi = 0;
+    if (lane == 0) bi = ld_relaxed_u32(cr.head);
+    bi = __shfl_sync(0xffffffffu, bi, 0);
+    if (bi >= (unsigned)cr.nbi) return;
+    if (bi != ready_bi) {
+      // sample rows the y-block needs: the voxel rows of its quad-cells plus one
+      const int y_lo = (int)fast_div(bi * CB_THREADS, g.wq_mul, g.wq_sh);
+      int q_hi = (int)bi * CB_THREADS + CB_THREADS - 1;
+      if (q_hi > g.quads_per_row - 1) q_hi = g.quads_per_row - 1;
+      const int y_hi = (int)fast_div((unsigned)q_hi, g.wq_mul, g.wq_sh) + 1;
+      bool ready = true;
+      for (int y = y_lo + lane; y <= y_hi; y += 32) ready = ready && (int)(ld_acquire_u32(cr.rows_done + y) - cr.target) >= 0;
+      if (!__all_sync(0xffffffffu, ready)) {
+        __nanosleep(4000);
+        continue;
+      }
+      ready_bi = bi;
+    }
+    unsigned int x0 = 0;
+    if (lane == 0) x0 = atomicAdd(cr.next_x + bi, TM_CNT_BATCH);
+    x0 = __shfl_sync(0xffffffffu, x0, 0);
+    if (x0 >= nxv) {  // this y-block is handed out: move on
+      if (lane == 0) atomicMax(cr.head, bi + 1u);
+      continue;
+    }
+    const unsigned n = min(TM_CNT_BATCH, nxv - x0);
+    for (unsigned k = 0; k < n; ++k) {
+      const long long chunk = (long long)(x0 + k) * g.blocks_per_row + bi;
+      uint32_t nv, nf;
+      mc_count_chunk<true>(bits, g, chunk, nf_s, nv, nf);
+      if (lane == 0) cr.woff[2 * chunk] = nv, cr.woff[2 * chunk + 1] = nf;
+    }
+    if (lane == 0) atomicAdd(cr.head + 1, n);
+  }
+}
+
+__global__ void __launch_bounds__((TM_WARPS + TM_CNT_WARPS_MAX) * 32)
 signpack_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t* __restrict__ bits, int nx, int ny, int nz, int W,
-                    float thresh, int nxseg, long long ntasks, unsigned long long* __restrict__ clear, int nclear) {
+                    float thresh, int nxseg, int nzc, long long ntasks, unsigned long long* __restrict__ clear, int nclear,
+                    const __grid_constant__ CountRide cr) {
   extern __shared__ __align__(128) unsigned char tm_smem[];
   __shared__ __align__(8) uint64_t full[TM_WARPS][TM_STAGES];
+  __shared__ uint8_t nf_s[256];
+  __shared__ int cta_prog;  // z-words finished by the classify warps of this CTA (SP_ZW each)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   // block 0 resets the scan state (ticket + look-back chain) of the count/scan kernels that follow in the stream
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < nclear; i += blockDim.x) clear[i] = 0ull;
+  if (threadIdx.x == 0) cta_prog = 0;
+  if (cr.nbi > 0)
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) nf_s[i] = (uint8_t)((ISO_MC_VERTS[i] >> 52) & 7);
+  __syncthreads();
+  if (wib >= TM_WARPS) {  // ---- counting warps ----
+    if (cr.nbi > 0) count_ride(bits, cr, &cta_prog, nf_s);
+    return;
+  }
+  // ---- classify warps ----
   const long long task = (long long)blockIdx.x * TM_WARPS + wib;
-  if (task >= ntasks) return;
+  if (task >= ntasks) {
+    if (lane == 0) atomicAdd(&cta_prog, SP_ZW);
+    return;
+  }
   unsigned char* base = tm_smem + (128 - (smem_u32(tm_smem) & 127)) % 128 + (size_t)wib * TM_SMEM_PER_WARP;
   float* box = reinterpret_cast<float*>(base);                                                      // [TM_STAGES][TM_BZ][128]
   uint32_t* wstage = reinterpret_cast<uint32_t*>(base + (size_t)TM_STAGES * TM_BOX_FLOATS * 4);      // [SP_ZW][128]
+  // y-major task order: rows complete one after the other while the kernel runs (the counting warps follow them)
   const int xseg = (int)(task % nxseg);
   const long long t2 = task / nxseg;
-  const int y = (int)(t2 % ny);
-  const int zc = (int)(t2 / ny);
+  const int zc = (int)(t2 % nzc);
+  const int y = (int)(t2 / nzc);
   const int x0 = xseg * SP_XSEG, z0 = zc * SP_ZW * 32;
   // boxes of this task that contain at least one valid z-plane
   const int nbox = min(TM_BOXES, (nz - z0 + TM_BZ - 1) / TM_BZ);
@@ -116,6 +222,7 @@ signpack_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t* __restri
     if (((b + 1) * TM_BZ) % 32 == 0) {  // a z-word is complete
       *reinterpret_cast<uint4*>(&wstage[(b * TM_BZ / 32) * SP_XSEG + lane * 4]) = make_uint4(w0, w1, w2, w3);
       w0 = w1 = w2 = w3 = 0;
+      if (lane == 0) atomicAdd(&cta_prog, 1);
     }
   }
   // write-out, identical to signpack_kernel<true>: column j of this lane, SP_ZW words as 16-byte stores
@@ -135,6 +242,12 @@ signpack_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t* __restri
       for (int c4 = 0; c4 < SP_ZW; c4 += 4)
         if (wofs + c4 < W) *reinterpret_cast<uint4*>(dst + c4) = make_uint4(c[c4], c[c4 + 1], c[c4 + 2], c[c4 + 3]);
     }
+  }
+  // release: this task's words are visible before the row counter moves
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) {
+    if (cr.nbi > 0) atomicAdd(cr.rows_done + y, 1u);
   }
 }
 
