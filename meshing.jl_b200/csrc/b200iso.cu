@@ -100,6 +100,7 @@ struct b200iso_handle {
   // scan state, cleared by block 0 of the classify kernel: [0] = ticket, [2 ..) = look-back chain of the scan blocks
   DevBuf<unsigned long long> chain;
   DevBuf<unsigned long long> status;  // MT: inclusive (vertex, face) prefix of every generate block (FLAG_INC | value)
+  DevBuf<uint32_t> recs, nrecs;       // MC: active-voxel records of every generate block (REC_CAP each) and their number
   DevBuf<unsigned long long> woff;    // MC: exclusive (vertex, face) prefix of every generate block; MT: raw block totals
   DevBuf<double> coords;
   DevBuf<uint8_t> cases;             // b200iso_case_indices(HOST): device scratch, kept across calls
@@ -220,6 +221,9 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
   if (mt) {
     if (int rc = h->status.reserve((size_t)h->nblocks * 2)) return rc;
     if (int rc = h->celloff.reserve(nbits)) return rc;
+  } else {
+    if (int rc = h->recs.reserve((size_t)h->nblocks * iso::REC_CAP + 2)) return rc;
+    if (int rc = h->nrecs.reserve((size_t)h->nblocks)) return rc;
   }
   if (int rc = h->coords.reserve((size_t)(nx + ny + nz))) return rc;
   unsigned int* ticket = reinterpret_cast<unsigned int*>(h->chain.p);
@@ -257,6 +261,7 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
           CU(cudaMemsetAsync(h->ride.p, 0, words * sizeof(unsigned int), st));
           h->ride_ny = ny, h->ride_tpr = tpr, h->ride_nbi = nbi, h->ride_step = 0;
         }
+        cr.recs = h->recs.p, cr.nrecs = h->nrecs.p;
         cr.nbi = (int)nbi, cr.woff = h->woff.p, cr.head = h->ride.p, cr.next_x = h->ride.p + iso::RIDE_HDR;
         cr.rows_done = cr.next_x + nbi;
         cr.target = ++h->ride_step * (unsigned int)tpr;
@@ -288,7 +293,7 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
   if (!mt) {
     const unsigned ncb = (unsigned)((h->nblocks + iso::WC_THREADS / 32 - 1) / (iso::WC_THREADS / 32));
     // (after a classify with counting warps only the items they did not claim are left: blocks beyond them exit at once)
-    iso::mc_count_chunks_kernel<<<ncb, iso::WC_THREADS, 0, st>>>(h->bits.p, g, h->nblocks, h->woff.p, ride ? h->ride.p + iso::RIDE_HDR : nullptr);
+    iso::mc_count_chunks_kernel<<<ncb, iso::WC_THREADS, 0, st>>>(h->bits.p, g, h->nblocks, h->woff.p, h->recs.p, h->nrecs.p, ride ? h->ride.p + iso::RIDE_HDR : nullptr);
     CU(cudaGetLastError());
     iso::mc_scan_chunks_kernel<<<(unsigned)nsb, iso::SC_THREADS, 0, st>>>(h->woff.p, h->nblocks, chain, ticket, nsb, h->totals_dev, totals_out,
                                                                           ride ? h->ride.p : nullptr, ride ? iso::RIDE_HDR + g.blocks_per_row : 0);
@@ -334,6 +339,7 @@ int enqueue_generate(b200iso_handle* h, void* verts_dev, int64_t vcap, int64_t* 
     a.iso_d = p.iso, a.iso_f = (float)p.iso, a.eps_d = p.eps, a.eps_f = (float)p.eps;
     a.iso_is_f32 = p.iso_is_f32, a.eps_is_f32 = p.eps_is_f32, a.p_is_f32 = p.range_kind == B200ISO_RANGE_F32;
     a.sdf_vec = !p.field_is_f64 && h->grid.ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(h->sdf_dev) & 15) == 0;
+    a.recs = h->recs.p, a.nrecs = h->nrecs.p;
     a.nblocks = h->nblocks, a.totals_a = h->totals_dev, a.abort_flag = h->totals_dev + 2;
     const unsigned nb = (unsigned)h->nblocks;
     const bool pf32 = p.range_kind == B200ISO_RANGE_F32;
@@ -416,7 +422,7 @@ int b200iso_destroy(b200iso_handle* h) {
   for (cudaEvent_t e : h->slab_ev) cudaEventDestroy(e);
   h->pool.release();
   h->bits.release(), h->celloff.release(), h->woff.release(), h->chain.release(), h->status.release(), h->coords.release(), h->field.release(), h->vstage.release(), h->fstage.release();
-  h->cases.release(), h->ride.release();
+  h->cases.release(), h->ride.release(), h->recs.release(), h->nrecs.release();
   if (h->totals_dev) cudaFree(h->totals_dev);
   if (h->totals_host) cudaFreeHost(h->totals_host);
   if (h->ev) {

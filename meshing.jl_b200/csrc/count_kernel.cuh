@@ -86,12 +86,12 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
   return v;
 }
 
-// (launch bound 6 blocks/SM = 40 registers, 75 % occupancy: 0.171 ms against 0.174 at 5 and 0.179 at 4 blocks/SM)
+// (launch bound 4 blocks/SM = 64 registers: with the record emission 40 registers spill 200+ bytes)
 // next_x: the counting warps inside the TMA classify kernel (signpack_tma.cuh) have already counted, of every y-block
 // bi, the generate blocks x < next_x[bi]; this kernel takes the rest (everything when next_x == nullptr).
-__global__ void __launch_bounds__(WC_THREADS, 6)
+__global__ void __launch_bounds__(WC_THREADS, 4)
 mc_count_chunks_kernel(const uint32_t* __restrict__ bits, Grid g, long long nchunks, unsigned long long* __restrict__ woff,
-                       const unsigned int* __restrict__ next_x) {
+                       uint32_t* __restrict__ recs, uint32_t* __restrict__ nrecs, const unsigned int* __restrict__ next_x) {
   __shared__ uint8_t nf_s[256];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // items are numbered y-block-major: item = bi * nxv + x
@@ -116,7 +116,7 @@ mc_count_chunks_kernel(const uint32_t* __restrict__ bits, Grid g, long long nchu
   if (next_x && x < (long long)__ldg(next_x + bi)) return;  // counted inside the classify kernel
   const long long chunk = x * g.blocks_per_row + bi;
   uint32_t nv, nf;
-  mc_count_chunk<false>(bits, g, chunk, nf_s, nv, nf);
+  mc_count_chunk<false>(bits, g, chunk, nf_s, recs, nrecs, nv, nf);
   if (lane == 0) woff[2 * chunk] = nv, woff[2 * chunk + 1] = nf;
 }
 

@@ -338,27 +338,54 @@ __device__ __forceinline__ uint32_t mc_nverts_masked(const Quad& q, int i, uint3
 // Marching Cubes count of one generate block ("chunk": CB_THREADS consecutive quad-cells of one voxel x-row), by ONE
 // warp: lane <-> quad-cell, 32 at a time.  vertices = crossed cube edges (12 masked popcounts per word), faces = table
 // look-up per active voxel (nf_s: 256-byte table in shared memory).  Returns the chunk's totals in every lane.
+// While it is there the count also leaves the block's ACTIVE-VOXEL RECORDS for generate (scan order, 4 bytes each:
+// case | voxel-in-quad-cell << 8 | quad-cell-in-block << 15), up to REC_CAP per block, and the number of active voxels
+// in nrecs[chunk].  generate then starts from the records instead of re-deriving them from the bit-field (its
+// thread mapping, quad-cell loads, active masks, block scan and case extraction were a third of its instructions);
+// a block with more than REC_CAP active voxels (dense fields) takes generate's own front end instead.
+constexpr int REC_CAP = 512;  // records per generate block (2 KB): 3 % of its 16384 voxels; the 1024^3 gyroid averages 155
 template <bool CG>
 __device__ __forceinline__ void mc_count_chunk(const uint32_t* __restrict__ bits, const Grid& g, long long chunk, const uint8_t* nf_s,
-                                               uint32_t& nv_out, uint32_t& nf_out) {
+                                               uint32_t* __restrict__ recs, uint32_t* __restrict__ nrecs, uint32_t& nv_out, uint32_t& nf_out) {
   const int lane = threadIdx.x & 31;
-  uint32_t nv = 0, nf = 0;
+  uint32_t nv = 0, nf = 0, base = 0;  // base: active voxels of the block before this group of 32 quad-cells (uniform)
   const int x = (int)(chunk / g.blocks_per_row);
   const int q_lo = (int)(chunk - (long long)x * g.blocks_per_row) * CB_THREADS;
+  uint32_t* rec = recs + chunk * REC_CAP;
   for (int q0 = q_lo; q0 < q_lo + CB_THREADS && q0 < g.quads_per_row; q0 += 32) {
     const int qr = q0 + lane;
     const int y = (int)fast_div((unsigned)qr, g.wq_mul, g.wq_sh), zq = qr - y * g.Wq;
     Quad q;
-    if (qr < g.quads_per_row && load_quad<CG>(bits, g, x, y, zq, q)) {
+    const bool act = qr < g.quads_per_row && load_quad<CG>(bits, g, x, y, zq, q);
+    uint32_t mm[4] = {0, 0, 0, 0}, na = 0;
+    if (act) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mm[i] = active_mask(q, i), na += __popc(mm[i]);
+    }
+    if (!__any_sync(0xffffffffu, na != 0)) continue;  // (uniform)
+    // position of this lane's first record: exclusive scan over the lanes (lane order == scan order)
+    uint32_t inc = na;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    uint32_t pos = base + inc - na;
+    base += __shfl_sync(0xffffffffu, inc, 31);
+    if (na) {
+      const uint32_t qtag = (uint32_t)(qr - q_lo) << 15;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        uint32_t mm = active_mask(q, i);
-        if (mm) {
+        uint32_t m = mm[i];
+        if (m) {
           nv += mc_nverts_masked(q, i, q.vm[i]);
-          while (mm) {
-            const int k = __ffs(mm) - 1;
-            mm &= mm - 1;
-            nf += nf_s[case_of<0>(q, i, k)];
+          while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t c = case_of<0>(q, i, k);
+            nf += nf_s[c];
+            if (pos < (uint32_t)REC_CAP) rec[pos] = c | ((uint32_t)(i * 32 + k) << 8) | qtag;
+            ++pos;
           }
         }
       }
@@ -369,6 +396,7 @@ __device__ __forceinline__ void mc_count_chunk(const uint32_t* __restrict__ bits
     nv += __shfl_xor_sync(0xffffffffu, nv, o);
     nf += __shfl_xor_sync(0xffffffffu, nf, o);
   }
+  if (lane == 0) nrecs[chunk] = base;
   nv_out = nv, nf_out = nf;
 }
 
@@ -591,6 +619,8 @@ struct GenArgs {
   double eps_d;
   int iso_is_f32, eps_is_f32, p_is_f32;  // typeof(iso), typeof(eps), eltype of the points (ranges)
   int sdf_vec;                           // Float32 field, base 16-byte aligned, ldx % 4 == 0: aligned pair loads
+  const uint32_t* recs;          // MC: active-voxel records of every generate block (REC_CAP each), written by the count
+  const uint32_t* nrecs;         // MC: active voxels per generate block
   long long nblocks;
   const long long* totals_a;     // device totals {nverts, nfaces} of the count
   const long long* abort_flag;   // != 0: a peer exchange ahead of this kernel failed -- emit nothing
@@ -769,12 +799,24 @@ mc_generate_kernel(GenArgs a, Grid g) {
     if (bv == v1) return;
     bf = a.woff[2 * (unsigned long long)b + 1];
   }
-  const TMap tm = thread_map(g, b);
-  // ---- A: active voxels per thread, exclusive scan (thread order == scan order) ----
-  Quad q;
-  const uint32_t tna = count_active(a.bits, g, tm, q);
-  uint32_t blk_na;
-  const uint32_t my_a0 = block_excl_scan_u32(tna, s_w, blk_na);
+  // The count left the block's active-voxel records (scan order) unless there are more than REC_CAP of them: then
+  // (dense fields) this block derives them from the bit-field itself (A + B1a below).
+  const uint32_t nrec = __ldg(a.nrecs + b);
+  const bool from_recs = nrec <= (uint32_t)REC_CAP;  // (uniform over the block)
+  TMap tm;
+  tm.x = (int)fast_div(b, g.bpr_mul, g.bpr_sh);
+  const uint32_t q_lo = (b - (unsigned)tm.x * (unsigned)g.blocks_per_row) * CB_THREADS;  // first quad-cell of the block in its x-row
+  uint32_t tna = 0, my_a0 = 0, blk_na = nrec;
+  if (!from_recs) {
+    // ---- A: active voxels per thread, exclusive scan (thread order == scan order) ----
+    tm = thread_map(g, b);
+    Quad q;
+    tna = count_active(a.bits, g, tm, q);
+    my_a0 = block_excl_scan_u32(tna, s_w, blk_na);
+    // ---- B1a: records (position, case) of the first window's voxels, in scan order, from the quad-cell in registers
+    // (dead afterwards); later windows reload it
+    if (tna && my_a0 < (uint32_t)GEN_NB) push_records<0>(q, tm, my_a0, 0, min((uint32_t)GEN_NB, blk_na), reinterpret_cast<uint2*>(rec), 2);
+  }
   if (blk_na == 0) return;  // (cannot happen after the test above; kept as a guard)
 
   const long long vbase = a.vbase + (a.vbase_dev ? *a.vbase_dev : 0);
@@ -786,20 +828,17 @@ mc_generate_kernel(GenArgs a, Grid g) {
   const bool vwide = (reinterpret_cast<uintptr_t>(a.verts) & (2 * sizeof(V) - 1)) == 0;
   const bool fwide = (reinterpret_cast<uintptr_t>(a.faces) & 15) == 0;
 
-  // ---- B1a: records (position, case) of the window's voxels, in scan order; the case index of an active voxel is
-  //      computed exactly once, here.  The first window (the only one unless the block holds more than GEN_NB
-  //      active voxels) is pushed from the quad-cell in registers, which is dead afterwards; later windows reload it.
-  if (tna && my_a0 < (uint32_t)GEN_NB) push_records<0>(q, tm, my_a0, 0, min((uint32_t)GEN_NB, blk_na), reinterpret_cast<uint2*>(rec), 2);
-
   for (uint32_t lo = 0; lo < blk_na; lo += GEN_NB) {
     const uint32_t hi = min(lo + (uint32_t)GEN_NB, blk_na);
     const uint32_t cnt = hi - lo;
-    if (lo > 0 && tna && my_a0 < hi && my_a0 + tna > lo) {
-      Quad q2;
-      load_quad(a.bits, g, tm.x, tm.y, tm.zq, q2);
-      push_records<0>(q2, tm, my_a0, lo, hi, reinterpret_cast<uint2*>(rec), 2);
+    if (!from_recs) {
+      if (lo > 0 && tna && my_a0 < hi && my_a0 + tna > lo) {
+        Quad q2;
+        load_quad(a.bits, g, tm.x, tm.y, tm.zq, q2);
+        push_records<0>(q2, tm, my_a0, lo, hi, reinterpret_cast<uint2*>(rec), 2);
+      }
+      __syncthreads();
     }
-    __syncthreads();
     // ---- B1b: two records per thread: tables -> counts -> scan -> owner maps; gather the corner samples.
     // z-adjacent records (same column, z + 1: adjacent in scan order) share a sample plane: the lower plane of the
     // second is the upper plane of the first -- taken from registers (in-thread pair) or from the lane below
@@ -807,8 +846,23 @@ mc_generate_kernel(GenArgs a, Grid g) {
     const uint32_t r0 = 2 * tid, r1 = r0 + 1;
     uint32_t nvf0 = 0, nvf1 = 0;  // vertices | faces << 16 of the two records
     uint32_t yz0 = 0xffffffffu, yz1 = 0xfffffffeu;
+    uint2 rc0 = make_uint2(0, 0), rc1 = make_uint2(0, 0);  // (y | z << 16, case) of the two records
+    if (from_recs) {
+      // the count's records: case | voxel-in-quad-cell << 8 | quad-cell-in-block << 15 (one aligned 8-byte load per thread)
+      const uint2 w = r0 < cnt ? __ldg(reinterpret_cast<const uint2*>(a.recs + (unsigned long long)b * REC_CAP + lo + r0)) : make_uint2(0, 0);
+      auto decode = [&](uint32_t wd) {
+        const uint32_t qr = q_lo + (wd >> 15), y = fast_div(qr, g.wq_mul, g.wq_sh), zq = qr - y * (uint32_t)g.Wq;
+        return make_uint2(y | ((zq * 128u + ((wd >> 8) & 127u)) << 16), wd & 0xffu);
+      };
+      rc0 = decode(w.x), rc1 = decode(w.y);
+      if (r0 < cnt) rec[r0].x = rc0.x;
+      if (r1 < cnt) rec[r1].x = rc1.x;
+    } else {
+      if (r0 < cnt) rc0 = *reinterpret_cast<const uint2*>(&rec[r0]);
+      if (r1 < cnt) rc1 = *reinterpret_cast<const uint2*>(&rec[r1]);
+    }
     if (r0 < cnt) {
-      const uint2 rc = *reinterpret_cast<const uint2*>(&rec[r0]);
+      const uint2 rc = rc0;
       yz0 = rc.x;
       const unsigned long long tv = __ldg(&ISO_MC_VERTS[rc.y]);
       recf[r0] = __ldg(&ISO_MC_FACES[rc.y]);
@@ -816,7 +870,7 @@ mc_generate_kernel(GenArgs a, Grid g) {
       nvf0 = (uint32_t)((tv >> 48) & 15) | ((uint32_t)((tv >> 52) & 7) << 16);
     }
     if (r1 < cnt) {
-      const uint2 rc = *reinterpret_cast<const uint2*>(&rec[r1]);
+      const uint2 rc = rc1;
       yz1 = rc.x;
       const unsigned long long tv = __ldg(&ISO_MC_VERTS[rc.y]);
       recf[r1] = __ldg(&ISO_MC_FACES[rc.y]);

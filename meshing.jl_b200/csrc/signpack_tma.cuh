@@ -84,6 +84,8 @@ struct CountRide {
   Grid g;                      // geometry of the count (same as generate)
   int nbi;                     // y-blocks = generate blocks per voxel x-row; 0 = no counting warps
   unsigned long long* woff;    // raw (vertex, face) pair per generate block
+  uint32_t* recs;              // active-voxel records per generate block (REC_CAP each) ...
+  uint32_t* nrecs;             // ... and their number
   unsigned int* head;          // [0] cur_bi, [1] claimed
   unsigned int* next_x;        // [nbi]
   unsigned int* rows_done;     // [ny] finished classify tasks per sample row, cumulative over steps
@@ -142,7 +144,7 @@ __device__ __forceinline__ void count_ride(const uint32_t* __restrict__ bits, co
     for (unsigned k = 0; k < n; ++k) {
       const long long chunk = (long long)(x0 + k) * g.blocks_per_row + bi;
       uint32_t nv, nf;
-      mc_count_chunk<true>(bits, g, chunk, nf_s, nv, nf);
+      mc_count_chunk<true>(bits, g, chunk, nf_s, cr.recs, cr.nrecs, nv, nf);
       if (lane == 0) cr.woff[2 * chunk] = nv, cr.woff[2 * chunk + 1] = nf;
     }
     if (lane == 0) atomicAdd(cr.head + 1, n);
