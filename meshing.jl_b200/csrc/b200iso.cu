@@ -291,9 +291,12 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
   // (2) count (raw totals per generate block), then a light single-pass decoupled look-back scan over them
   h->totals_out = totals_out;
   if (!mt) {
-    const unsigned ncb = (unsigned)((h->nblocks + iso::WC_THREADS / 32 - 1) / (iso::WC_THREADS / 32));
-    // (after a classify with counting warps only the items they did not claim are left: blocks beyond them exit at once)
-    iso::mc_count_chunks_kernel<<<ncb, iso::WC_THREADS, 0, st>>>(h->bits.p, g, h->nblocks, h->woff.p, h->recs.p, h->nrecs.p, ride ? h->ride.p + iso::RIDE_HDR : nullptr);
+    // after a classify with counting warps only the last y-blocks are left: a quarter of the full grid, grid-stride
+    // (correct for any remainder), instead of thousands of blocks that look at the queue and leave
+    unsigned ncb = (unsigned)((h->nblocks + iso::WC_THREADS / 32 - 1) / (iso::WC_THREADS / 32));
+    if (ride) ncb = std::max(1u, std::min(ncb, std::max(148u * 4u, ncb / 4)));
+    static_assert(iso::RIDE_HDR_WORDS == iso::RIDE_HDR, "ride buffer layout");
+    iso::mc_count_chunks_kernel<<<ncb, iso::WC_THREADS, 0, st>>>(h->bits.p, g, h->nblocks, h->woff.p, h->recs.p, h->nrecs.p, ride ? h->ride.p : nullptr);
     CU(cudaGetLastError());
     iso::mc_scan_chunks_kernel<<<(unsigned)nsb, iso::SC_THREADS, 0, st>>>(h->woff.p, h->nblocks, chain, ticket, nsb, h->totals_dev, totals_out,
                                                                           ride ? h->ride.p : nullptr, ride ? iso::RIDE_HDR + g.blocks_per_row : 0);

@@ -87,37 +87,29 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 }
 
 // (launch bound 4 blocks/SM = 64 registers: with the record emission 40 registers spill 200+ bytes)
-// next_x: the counting warps inside the TMA classify kernel (signpack_tma.cuh) have already counted, of every y-block
-// bi, the generate blocks x < next_x[bi]; this kernel takes the rest (everything when next_x == nullptr).
+// ride: the counting warps inside the TMA classify kernel (signpack_tma.cuh) have already counted every y-block
+// below ride[0] (cur_bi) and, of the y-blocks from there on, the generate blocks x < next_x[bi]; this kernel takes the
+// rest with a grid-stride loop (everything, starting at item 0, when ride == nullptr).  Items are numbered
+// y-block-major: item = bi * nxv + x.
+constexpr int RIDE_HDR_WORDS = 32;  // == RIDE_HDR of signpack_tma.cuh: cur_bi, statistics, then next_x[]
 __global__ void __launch_bounds__(WC_THREADS, 4)
 mc_count_chunks_kernel(const uint32_t* __restrict__ bits, Grid g, long long nchunks, unsigned long long* __restrict__ woff,
-                       uint32_t* __restrict__ recs, uint32_t* __restrict__ nrecs, const unsigned int* __restrict__ next_x) {
+                       uint32_t* __restrict__ recs, uint32_t* __restrict__ nrecs, const unsigned int* __restrict__ ride) {
   __shared__ uint8_t nf_s[256];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // items are numbered y-block-major: item = bi * nxv + x
-  const long long item0 = (long long)blockIdx.x * (WC_THREADS / 32);
   const long long nxv = g.nx - 1;
-  if (next_x) {  // all of this block's items already counted?  (uniform over the block)
-    const long long last = min(item0 + WC_THREADS / 32, nchunks) - 1;
-    const long long b0 = item0 / nxv, b1 = last / nxv;
-    bool todo = false;
-    for (long long bi = b0; bi <= b1; ++bi) {
-      const long long xa = bi == b0 ? item0 - b0 * nxv : 0, xb = bi == b1 ? last - b1 * nxv : nxv - 1;  // x range of the block in bi
-      todo = todo || (long long)__ldg(next_x + bi) <= xb;
-      (void)xa;
-    }
-    if (!todo) return;
-  }
+  const long long first = ride ? (long long)__ldg(ride) * nxv : 0ll;
+  if (first + (long long)blockIdx.x * (WC_THREADS / 32) >= nchunks) return;  // (uniform over the block)
   nf_s[threadIdx.x] = (uint8_t)((ISO_MC_VERTS[threadIdx.x] >> 52) & 7);
   __syncthreads();
-  const long long item = item0 + w;
-  if (item >= nchunks) return;
-  const long long bi = item / nxv, x = item - bi * nxv;
-  if (next_x && x < (long long)__ldg(next_x + bi)) return;  // counted inside the classify kernel
-  const long long chunk = x * g.blocks_per_row + bi;
-  uint32_t nv, nf;
-  mc_count_chunk<false>(bits, g, chunk, nf_s, recs, nrecs, nv, nf);
-  if (lane == 0) woff[2 * chunk] = nv, woff[2 * chunk + 1] = nf;
+  for (long long item = first + (long long)blockIdx.x * (WC_THREADS / 32) + w; item < nchunks; item += (long long)gridDim.x * (WC_THREADS / 32)) {
+    const long long bi = item / nxv, x = item - bi * nxv;
+    if (ride && x < (long long)__ldg(ride + RIDE_HDR_WORDS + bi)) continue;  // counted inside the classify kernel
+    const long long chunk = x * g.blocks_per_row + bi;
+    uint32_t nv, nf;
+    mc_count_chunk<false>(bits, g, chunk, nf_s, recs, nrecs, nv, nf);
+    if (lane == 0) woff[2 * chunk] = nv, woff[2 * chunk + 1] = nf;
+  }
 }
 
 constexpr int SC_THREADS = 256, SC_PER = 4;  // scan block: 1024 (vertex, face) pairs

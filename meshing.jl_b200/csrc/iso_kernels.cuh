@@ -898,14 +898,31 @@ mc_generate_kernel(GenArgs a, Grid g) {
       const Plane<T> below = shfl_up_plane<T>(U1);  // (all lanes take part)
       if (adj0) L0 = below;
       if (adj1) L1 = U0;
-      // MC corner order (src/marching_cubes.jl:42-49): 0 (0,0,0) 1 (1,0,0) 2 (1,1,0) 3 (0,1,0), then the same at z + 1
-      if (r0 < cnt) {
-        corner[r0][0] = L0.a00, corner[r0][1] = L0.a10, corner[r0][2] = L0.a11, corner[r0][3] = L0.a01;
-        corner[r0][4] = U0.a00, corner[r0][5] = U0.a10, corner[r0][6] = U0.a11, corner[r0][7] = U0.a01;
-      }
-      if (r1 < cnt) {
-        corner[r1][0] = L1.a00, corner[r1][1] = L1.a10, corner[r1][2] = L1.a11, corner[r1][3] = L1.a01;
-        corner[r1][4] = U1.a00, corner[r1][5] = U1.a10, corner[r1][6] = U1.a11, corner[r1][7] = U1.a01;
+      // MC corner order (src/marching_cubes.jl:42-49): 0 (0,0,0) 1 (1,0,0) 2 (1,1,0) 3 (0,1,0), then the same at z + 1.
+      // A thread's two records are 4 chunks of 16 bytes; chunk c of thread t lives at chunk c ^ ((t >> 1) & 3) of the
+      // thread's 64 bytes, so that the 8 lanes of a quarter-warp hit 8 different bank groups (unswizzled: 4-way conflicts).
+      {
+        float4* crow = reinterpret_cast<float4*>(&corner[r0][0]);  // (T = double: 8 chunks of 16 bytes, same rule on pairs)
+        const int sw = (tid >> 1) & 3;
+        if constexpr (sizeof(T) == 4) {
+          if (r0 < cnt) {
+            crow[0 ^ sw] = make_float4(L0.a00, L0.a10, L0.a11, L0.a01);
+            crow[1 ^ sw] = make_float4(U0.a00, U0.a10, U0.a11, U0.a01);
+          }
+          if (r1 < cnt) {
+            crow[2 ^ sw] = make_float4(L1.a00, L1.a10, L1.a11, L1.a01);
+            crow[3 ^ sw] = make_float4(U1.a00, U1.a10, U1.a11, U1.a01);
+          }
+        } else {
+          if (r0 < cnt) {
+            corner[r0][0] = L0.a00, corner[r0][1] = L0.a10, corner[r0][2] = L0.a11, corner[r0][3] = L0.a01;
+            corner[r0][4] = U0.a00, corner[r0][5] = U0.a10, corner[r0][6] = U0.a11, corner[r0][7] = U0.a01;
+          }
+          if (r1 < cnt) {
+            corner[r1][0] = L1.a00, corner[r1][1] = L1.a10, corner[r1][2] = L1.a11, corner[r1][3] = L1.a01;
+            corner[r1][4] = U1.a00, corner[r1][5] = U1.a10, corner[r1][6] = U1.a11, corner[r1][7] = U1.a01;
+          }
+        }
       }
     }
     uint32_t wtot;
@@ -940,7 +957,14 @@ mc_generate_kernel(GenArgs a, Grid g) {
       const uint32_t ca = e & 7u, cb = e < 8u ? ((e & 4u) | ((e + 1u) & 3u)) : e - 4u;
       // MC corner offsets (dx | dy<<1 | dz<<2) for corners 0..7: 0,1,3,2,4,5,7,6
       const uint32_t oa = (0x67542310u >> (4 * ca)) & 7u, ob = (0x67542310u >> (4 * cb)) & 7u;
-      const T va = corner[s][ca], vb = corner[s][cb];
+      T va, vb;
+      if constexpr (sizeof(T) == 4) {  // (chunk swizzle of the corner store, see B1b)
+        const T* cp = &corner[s & ~1u][0];
+        const uint32_t sw = (s >> 2) & 3u, hb = 2u * (s & 1u);
+        va = cp[(((hb + (ca >> 2)) ^ sw) << 2) + (ca & 3u)], vb = cp[(((hb + (cb >> 2)) ^ sw) << 2) + (cb & 3u)];
+      } else {
+        va = corner[s][ca], vb = corner[s][cb];
+      }
       const unsigned vy = yofs + (r.x & 0xffffu), vz = zofs + (r.x >> 16);
       double pa[3], pb[3];
       pa[0] = (oa & 1u) ? x1d : x0d;
