@@ -187,6 +187,16 @@ int b200iso_exchange_async(b200iso_handle* h, int64_t* bases_dev, int64_t* all_d
 int b200iso_extract_host(b200iso_handle* h, const b200iso_params* p, const void* sdf, int64_t nx, int64_t ny,
                          int64_t nz, int64_t ldx, void* verts, int64_t vcap, int64_t* faces, int64_t fcap,
                          int64_t* nverts, int64_t* nfaces, int* vert_is_f64);
+/* b200iso_extract_host_resident: finishes a b200iso_extract_host call that returned B200ISO_ECAPACITY (or was a pure
+ *                       count, vcap = fcap = 0) WITHOUT uploading the field again: the x-slabs are still resident on
+ *                       the device, only the kernels (milliseconds) and the device->host copy of the mesh run.  This
+ *                       is how the drop-in `isosurface(::Array)` works: one b200iso_extract_host into
+ *                       arrays sized by a guess -- the previous call's totals or a surface-area estimate; the mesh
+ *                       then streams out while the field still streams in -- and, only if the guess was short, this
+ *                       call into arrays of the exact size.  B200ISO_ESTATE if nothing is resident (any other
+ *                       host-field call on the handle in between invalidates the slabs). */
+int b200iso_extract_host_resident(b200iso_handle* h, void* verts, int64_t vcap, int64_t* faces, int64_t fcap,
+                                  int64_t* nverts, int64_t* nfaces);
 
 /* ---- parity / introspection ----------------------------------------------------------------------------
  * Per-voxel case index (_get_cubeindex, src/common.jl:10-20; corner order of the counted algo) for the

@@ -135,10 +135,16 @@ def isosurface(sdf, *args, device=None, capacity=None):
                tensors too and nothing crosses PCIe).
     method   : MarchingCubes(iso=...) (default) or MarchingTetrahedra(iso=..., eps=...)
     X, Y, Z  : ranges whose first/last elements give the extent; default -1:1 on every axis
-    capacity : optional (max_vertices, max_faces) guess for a host field: one-shot slab-pipelined call
-               (b200iso_extract_host) instead of count + generate; same result
+    capacity : optional (max_vertices, max_faces) for a host field instead of the built-in guess (see below)
     returns  : vertices (nverts, 3) Float32|Float64 by the reference's promotion rule, faces (nfaces, 3)
                int64, 1-based, in the reference's order (x-outermost, z-innermost voxel scan).
+
+    A host field takes the one-shot slab pipeline (b200iso_extract_host): the mesh streams out of the GPU while the
+    field still streams in.  The output arrays must exist before the mesh size is known, so they are allocated from
+    a guess -- the totals of the previous call with the same shape and method, else a surface-area estimate -- and
+    trimmed afterwards (untouched pages of the over-allocation are never backed by memory).  If the guess was short
+    the mesh is fetched into arrays of the exact size from the slabs still resident on the device
+    (b200iso_extract_host_resident): the field is uploaded once in every case.
     """
     if args and isinstance(args[0], (MarchingCubes, MarchingTetrahedra)):
         method, rest = args[0], args[1:]
@@ -159,23 +165,60 @@ def isosurface(sdf, *args, device=None, capacity=None):
     params.field_is_f64 = int(a.dtype == np.float64)
     nx, ny, nz = a.shape
     h = get_handle(0 if device is None else device)
-    if capacity is not None:
-        # one-shot slab pipeline (b200iso_extract_host): H2D, kernels and D2H overlap; exact re-run if the guess was short
-        f64 = _vert_is_f64(params)
-        vcap, fcap = int(capacity[0]), int(capacity[1])
-        for _ in range(2):
-            verts = np.empty((vcap, 3), dtype=np.float64 if f64 else np.float32)
-            faces = np.empty((fcap, 3), dtype=np.int64)
-            nv, nf, f64, fits = h.extract_host(params, a.ctypes.data, nx, ny, nz, nx, verts.ctypes.data, vcap, faces.ctypes.data, fcap)
-            if fits:
-                return verts[:nv], faces[:nf]
-            vcap, fcap = nv, nf
-        raise RuntimeError("b200iso_extract_host: capacity still too small after an exact re-run")
+    f64 = _vert_is_f64(params)
+    key = (h.device, a.shape, a.dtype.str, params.algo)
+    vcap, fcap = (int(capacity[0]), int(capacity[1])) if capacity is not None else _capacity_guess(key, a.shape, params.algo)
+    verts = np.empty((vcap, 3), dtype=np.float64 if f64 else np.float32)
+    faces = np.empty((fcap, 3), dtype=np.int64)
+    nv, nf, f64, fits = h.extract_host(params, a.ctypes.data, nx, ny, nz, nx, verts.ctypes.data, vcap, faces.ctypes.data, fcap)
+    if not fits:  # the guess was short: exact arrays, filled from the slabs that are still on the device
+        verts = np.empty((nv, 3), dtype=np.float64 if f64 else np.float32)
+        faces = np.empty((nf, 3), dtype=np.int64)
+        nv2, nf2, fits = h.extract_host_resident(verts.ctypes.data, nv, faces.ctypes.data, nf)
+        if not fits or (nv2, nf2) != (nv, nf):
+            raise RuntimeError("b200iso_extract_host_resident: totals changed between the two passes")
+    _capacity_memo[key] = (nv, nf)
+    return verts[:nv], faces[:nf]
+
+
+def isosurface_two_phase(sdf, *args, device=None):
+    """The same result through the two-phase pair of the C ABI -- b200iso_count (upload, classify, count: the caller
+    learns the sizes) then b200iso_generate into exact arrays -- i.e. without overlap between the upload and the
+    download.  Kept as a public form (a caller that cannot over-allocate) and as the cross-check of the one-shot path."""
+    if args and isinstance(args[0], (MarchingCubes, MarchingTetrahedra)):
+        method, rest = args[0], args[1:]
+    else:
+        method, rest = MarchingCubes(), args
+    params = make_params(method, *rest)
+    a = np.asfortranarray(np.asarray(sdf))
+    if a.ndim != 3 or a.dtype not in (np.float32, np.float64):
+        raise TypeError("3-D Float32/Float64 field expected")
+    params.field_is_f64 = int(a.dtype == np.float64)
+    nx, ny, nz = a.shape
+    h = get_handle(0 if device is None else device)
     nv, nf, f64 = h.count(params, a.ctypes.data, capi.HOST, nx, ny, nz, nx)
     verts = np.empty((nv, 3), dtype=np.float64 if f64 else np.float32)
     faces = np.empty((nf, 3), dtype=np.int64)
     h.generate(verts.ctypes.data, faces.ctypes.data, capi.HOST, 0)
     return verts, faces
+
+
+_capacity_memo = {}
+
+
+def _capacity_guess(key, shape, algo):
+    """(max_vertices, max_faces) for the one-shot call before the mesh size is known: the previous totals for this
+    shape and method plus 1/8, else an estimate from the surface area an isosurface of this grid typically has
+    (the 1024^3 gyroid of the benchmark: 38.7 n^2 MC vertices, 19.3 n^2 faces; MT 27.7 n^2 / 55.2 n^2)."""
+    memo = _capacity_memo.get(key)
+    if memo is not None:
+        return memo[0] + memo[0] // 8 + 1024, memo[1] + memo[1] // 8 + 1024
+    nx, ny, nz = (max(int(d) - 1, 0) for d in shape)
+    area = (nx * ny + ny * nz + nx * nz) / 3.0
+    nvox = nx * ny * nz
+    if algo == capi.MC:
+        return int(min(64 * area, 12 * nvox)) + 1024, int(min(32 * area, 5 * nvox)) + 1024
+    return int(min(48 * area, 7 * nvox)) + 1024, int(min(96 * area, 12 * nvox)) + 1024
 
 
 def _vert_is_f64(params):

@@ -76,6 +76,7 @@ def load():
     L.b200iso_totals.argtypes = [vp, pi64, pi64, pci]
     L.b200iso_extract_async.argtypes = [vp, pp, vp, i64, i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]
     L.b200iso_extract_host.argtypes = [vp, pp, vp, i64, i64, i64, i64, vp, i64, vp, i64, pi64, pi64, pci]
+    L.b200iso_extract_host_resident.argtypes = [vp, vp, i64, vp, i64, pi64, pi64]
     L.b200iso_set_peer_exchange.argtypes = [vp, ci, ci, ctypes.POINTER(vp)]
     L.b200iso_exchange_async.argtypes = [vp, vp, vp]
     L.b200iso_add_vertex_base_async.argtypes = [vp, vp, i64, vp, vp]
@@ -161,6 +162,16 @@ class Handle:
         if rc != ECAPACITY:
             _check(rc)
         return nv.value, nf.value, bool(f64.value), rc == 0
+
+    def extract_host_resident(self, verts_ptr, vcap, faces_ptr, fcap):
+        """Finish an extract_host call whose capacities were short from the slabs still resident on the device.
+        Returns (nverts, nfaces, fits)."""
+        nv, nf = ctypes.c_int64(), ctypes.c_int64()
+        rc = self.L.b200iso_extract_host_resident(self.h, ctypes.c_void_p(verts_ptr or 0), vcap, ctypes.c_void_p(faces_ptr or 0), fcap,
+                                                  ctypes.byref(nv), ctypes.byref(nf))
+        if rc != ECAPACITY:
+            _check(rc)
+        return nv.value, nf.value, rc == 0
 
     def set_peer_exchange(self, rank, world, slot_ptrs):
         """slot_ptrs[r] = device pointer (valid on this device) of rank r's PEER_BYTES exchange buffer; None switches it off."""

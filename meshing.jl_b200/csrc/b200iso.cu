@@ -126,6 +126,15 @@ struct b200iso_handle {
   DevBuf<long long> fstage1;
   hostpipe::Pool pool;             // copy lanes (streams, pinned chunks, events) of the HOST paths
   std::vector<cudaEvent_t> slab_ev;  // b200iso_extract_host: slab k generated; [n-2] fork, [n-1] join
+  // the x-slab sub-problems of the last b200iso_extract_host, resident in `field` (b200iso_extract_host_resident)
+  struct HostSlab {
+    b200iso_params prm;
+    const void* dev = nullptr;
+    int64_t nx = 0, ldx = 0;
+  };
+  std::vector<HostSlab> hs;
+  int64_t hs_ny = 0, hs_nz = 0, hs_nv = 0, hs_nf = 0;
+  int hs_vf64 = 0;
   long long* totals_dev = nullptr;   // device int64[4]: nverts, nfaces, peer-exchange error flag, spare
   // sharded path: peer exchange of the slab totals (b200iso_set_peer_exchange)
   iso::PeerSlots peers{};
@@ -239,21 +248,28 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
     const bool f64 = p->field_is_f64 != 0;
     const bool vec = !f64 && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(sdf_dev) & 15) == 0);
     const float* sdf_f = reinterpret_cast<const float*>(sdf_dev);
-    const int nxseg = (int)((nx + iso::SP_XSEG - 1) / iso::SP_XSEG);
+    int nxseg = (int)((nx + iso::SP_XSEG - 1) / iso::SP_XSEG);
     const int nzc = (g.W + iso::SP_ZW - 1) / iso::SP_ZW;
-    const long long ntasks = (long long)nxseg * ny * nzc;
+    long long ntasks = (long long)nxseg * ny * nzc;
     const unsigned nb = (unsigned)((ntasks + iso::SP_WARPS - 1) / iso::SP_WARPS);
     const float thr = threshold_for(p->iso, p->iso_is_f32 != 0);
     CUtensorMap tmap;
     // (measured: TMA wins on big fields -- 0.656 vs 0.694 ms at 1024^3 -- and loses a few % when the grid is under two waves)
     const bool tma_wanted = h->tma_mode == 1 || (h->tma_mode < 0 && ntasks >= 4096);
     if (vec && tma_wanted && iso::make_field_tmap(&tmap, sdf_f, nx, ny, nz, ldx)) {
+      // x-slabs with their halo plane have 128 k + 1 samples: the few columns beyond a multiple of 128 go through the
+      // tail path of the kernel (one pseudo-segment) instead of a 128-wide box each
+      const int rem = (int)(nx % iso::SP_XSEG);
+      const int ntail = (nx > iso::SP_XSEG && rem > 0 && rem <= iso::TM_TAIL_MAX) ? rem : 0;
+      if (ntail) --nxseg;  // (TMA segments; the tail tasks, one per row and z-chunk, are numbered first)
+      const long long tpr = (long long)(nxseg + (ntail ? 1 : 0)) * nzc;  // classify tasks per sample row
+      ntasks = tpr * ny;
       // TMA-staged classify: same tasks, cp.async.bulk.tensor boxes + per-warp mbarrier pipeline; for Marching Cubes
       // its CTAs carry counting warps that count the generate blocks while the field streams (signpack_tma.cuh)
       iso::CountRide cr{};
       cr.g = g;
       if (!mt && h->ride_warps > 0) {
-        const long long tpr = (long long)nxseg * nzc, nbi = g.blocks_per_row;
+        const long long nbi = g.blocks_per_row;
         const size_t words = (size_t)iso::RIDE_HDR + (size_t)nbi + (size_t)ny;
         if (int rc = h->ride.reserve(words)) return rc;
         if (h->ride_ny != ny || h->ride_tpr != tpr || h->ride_nbi != nbi ||
@@ -270,7 +286,7 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
       }
       const unsigned tb = (unsigned)((ntasks + iso::TM_WARPS - 1) / iso::TM_WARPS);
       iso::signpack_tma_kernel<<<tb, (iso::TM_WARPS + (ride ? h->ride_warps : 0)) * 32, iso::TM_SMEM, st>>>(tmap, h->bits.p, g.nx, g.ny, g.nz, g.W, thr, nxseg, nzc,
-                                                                                                  ntasks, h->chain.p, nclear, cr);
+                                                                                                  ntasks, h->chain.p, nclear, cr, sdf_f, g.ldx, ntail);
       h->classify_path = B200ISO_CLASSIFY_TMA;
     } else if (vec) {
       iso::signpack_kernel<true, float><<<nb, iso::SP_WARPS * 32, 0, st>>>(sdf_f, h->bits.p, g.nx, g.ny, g.nz, g.ldx, g.W, thr, nxseg, ntasks, h->chain.p, nclear);
@@ -583,6 +599,7 @@ static int b200iso_count_impl(b200iso_handle* h, const b200iso_params* p, const 
   const size_t esz = p->field_is_f64 ? 8 : 4;
   const bool staged = mem == B200ISO_HOST && nx * ny * nz > 0;
   if (staged) {
+    h->hs.clear();  // (the staging buffer is about to be overwritten: nothing resident for b200iso_extract_host_resident)
     // stage with a 16-byte aligned leading dimension so the 128-bit load path always applies
     dldx = (nx + 3) / 4 * 4;
     if (int rc = h->field.reserve((size_t)dldx * ny * nz * esz)) return rc;
@@ -687,6 +704,60 @@ int b200iso_generate(b200iso_handle* h, void* verts, int64_t* faces, int mem, in
 //               overlapping the H2D of the slabs behind it (PCIe is full duplex)
 // Every slab is the sharded sub-problem of api.isosurface_slab (x_offset / nx_global / vertex base; Marching
 // Tetrahedra slabs carry their ghost row), so the concatenation is byte-identical to the unsharded mesh.
+// Per-slab pass of the one-shot host forms: count (after the slab has arrived, when `up` is given), totals, generate into
+// a staging set, D2H into the final offsets of the caller's arrays.  The slab decomposition (h->hs) stays in the handle
+// with the slabs resident in h->field, so that a call whose capacities were too small is finished by
+// b200iso_extract_host_resident without uploading the field again.
+static int host_slab_pass(b200iso_handle* h, hostpipe::Uploader* up, void* verts, int64_t vcap, int64_t* faces, int64_t fcap, int64_t* nverts,
+                          int64_t* nfaces) {
+  cudaStream_t st = h->stream;
+  const int S = (int)h->hs.size();
+  const size_t vsz = h->hs_vf64 ? 8 : 4;
+  const cudaEvent_t ev_fork = h->slab_ev[S];
+  hostpipe::Downloader down;
+  CU(down.start(&h->pool, S, hostpipe::is_pinned(verts) && hostpipe::is_pinned(faces), ev_fork));
+  int64_t cv = 0, cf = 0;
+  int njobs = 0;
+  bool overflow = false;
+  for (int k = 0; k < S; ++k) {
+    const b200iso_handle::HostSlab& hk = h->hs[k];
+    if (hk.nx < 2) continue;
+    if (up) {
+      CU(up->wait_slab(k, st));
+      if (k == S - 1)
+        if (int rc = h->rec(b200iso_handle::E_H1)) return rc;
+    }
+    if (int rc = enqueue_count(h, &hk.prm, hk.dev, hk.nx, h->hs_ny, h->hs_nz, hk.ldx, nullptr, true)) return rc;
+    if (int rc = fetch_totals(h)) return rc;
+    const int64_t nv = h->nverts, nf = h->nfaces;
+    if (cv + nv > vcap || cf + nf > fcap) overflow = true;
+    if (!overflow && (nv > 0 || nf > 0)) {
+      DevBuf<unsigned char>& vs = (njobs & 1) ? h->vstage1 : h->vstage;
+      DevBuf<long long>& fs = (njobs & 1) ? h->fstage1 : h->fstage;
+      if (njobs >= 2) CU(down.wait_job(njobs - 2));  // this staging set's previous D2H
+      if (int rc = vs.reserve((size_t)nv * 3 * vsz + 16)) return rc;
+      if (int rc = fs.reserve((size_t)nf * 3 + 2)) return rc;
+      if (int rc = enqueue_generate(h, vs.p, nv, (int64_t*)fs.p, nf, nullptr, cv)) return rc;
+      CU(cudaEventRecord(h->slab_ev[k], st));
+      hostpipe::Downloader::Job j;
+      j.src[0] = vs.p, j.dst[0] = (unsigned char*)verts + (size_t)cv * 3 * vsz, j.bytes[0] = (size_t)nv * 3 * vsz;
+      j.src[1] = (const unsigned char*)fs.p, j.dst[1] = (unsigned char*)(faces + (size_t)cf * 3), j.bytes[1] = (size_t)nf * 3 * sizeof(int64_t);
+      j.ready = h->slab_ev[k];
+      CU(down.push(njobs++, j));
+    }
+    cv += nv, cf += nf;
+  }
+  if (up) up->join();
+  CU(down.finish());  // the mesh is in the caller's arrays
+  CU(cudaStreamSynchronize(st));
+  h->counted = false;  // the handle holds the last slab only: not a state b200iso_generate may continue from
+  if (nverts) *nverts = cv;
+  if (nfaces) *nfaces = cf;
+  h->hs_nv = cv, h->hs_nf = cf;
+  if (overflow) return fail(B200ISO_ECAPACITY, "mesh has %lld vertices / %lld faces, capacity is %lld / %lld", (long long)cv, (long long)cf, (long long)vcap, (long long)fcap);
+  return 0;
+}
+
 static int b200iso_extract_host_impl(b200iso_handle* h, const b200iso_params* p, const void* sdf, int64_t nx, int64_t ny, int64_t nz,
                          int64_t ldx, void* verts, int64_t vcap, int64_t* faces, int64_t fcap, int64_t* nverts,
                          int64_t* nfaces, int* vert_is_f64) {
@@ -700,8 +771,10 @@ static int b200iso_extract_host_impl(b200iso_handle* h, const b200iso_params* p,
   if (vert_is_f64) *vert_is_f64 = f64;
   if (nverts) *nverts = 0;
   if (nfaces) *nfaces = 0;
+  h->hs.clear();
+  h->hs_nv = h->hs_nf = 0;
   if (nx < 2 || ny < 2 || nz < 2) return 0;  // zero voxels, empty mesh
-  const size_t esz = p->field_is_f64 ? 8 : 4, vsz = f64 ? 8 : 4;
+  const size_t esz = p->field_is_f64 ? 8 : 4;
   const bool mt = p->algo == B200ISO_MT;
   // slabs of >= 256 samples, at most 8, and only on big fields.  Measured at 1024^3 (pinned arrays, PCIe 5 x16):
   // 4 slabs 88.4 ms, 8 slabs 90.9, 16 slabs 98.8, 32 slabs 158 -- against 96.3 ms for count + generate; alone the
@@ -737,60 +810,55 @@ static int b200iso_extract_host_impl(b200iso_handle* h, const b200iso_params* p,
   }
   if (int rc = h->field.reserve(field_bytes)) return rc;
   for (hostpipe::Slab& sb : slabs) sb.dst = h->field.p + (size_t)sb.dst;
+  // the sub-problems (a caller's own slab of a sharded volume keeps its x_offset / nx_global / ghost row: sub-slab 0 inherits them)
+  h->hs.resize(S);
+  h->hs_ny = ny, h->hs_nz = nz, h->hs_vf64 = f64;
+  for (int k = 0; k < S; ++k) {
+    const int64_t a = bound[k], b = bound[k + 1];
+    b200iso_handle::HostSlab& hk = h->hs[k];
+    const int ghost = a > 0 ? (mt ? 1 : 0) : p->x_ghost;
+    hk.prm = *p;
+    hk.prm.x_offset = p->x_offset + a - (a > 0 ? ghost : 0), hk.prm.nx_global = p->nx_global > 0 ? p->nx_global : nx, hk.prm.x_ghost = ghost;
+    const int lo = a > 0 ? ghost : 0;  // sample planes below voxel row a that the sub-slab starts with
+    hk.nx = b > a ? b - a + 1 + lo : 0;
+    hk.dev = slabs[k].dst, hk.ldx = (int64_t)(slabs[k].dpitch / esz);
+  }
   cudaStream_t st = h->stream;
   const cudaEvent_t ev_fork = h->slab_ev[S];
   h->begin_step();
   if (int rc = h->rec(b200iso_handle::E_H0)) return rc;
   CU(cudaEventRecord(ev_fork, st));  // the copy lanes start after whatever the caller's stream holds
-  // (1) H2D, enqueued by the uploader's worker threads (the enqueue of a million-row 2-D copy keeps its thread busy
+  // H2D, enqueued by the uploader's worker threads (the enqueue of a million-row 2-D copy keeps its thread busy
   // for about the copy's duration, and this thread has the kernels and the D2H of the earlier slabs to enqueue).
   hostpipe::Uploader up;
-  hostpipe::Downloader down;
   CU(up.start(&h->pool, slabs, (const unsigned char*)sdf, (size_t)ldx * esz, esz, (size_t)ny * nz, ev_fork));
-  CU(down.start(&h->pool, S, hostpipe::is_pinned(verts) && hostpipe::is_pinned(faces), ev_fork));
-  // (2) per slab: count, totals, generate into staging set (job & 1), D2H into the final offsets
-  int64_t cv = 0, cf = 0;
-  int njobs = 0;
-  bool overflow = false;
-  for (int k = 0; k < S; ++k) {
-    const int64_t a = bound[k], b = bound[k + 1];
-    if (b <= a) continue;
-    // (a caller's own slab of a sharded volume keeps its x_offset / nx_global / ghost row: sub-slab 0 inherits them)
-    const int ghost = a > 0 ? (mt ? 1 : 0) : p->x_ghost;
-    b200iso_params pk = *p;
-    pk.x_offset = p->x_offset + a - (a > 0 ? ghost : 0), pk.nx_global = p->nx_global > 0 ? p->nx_global : nx, pk.x_ghost = ghost;
-    const int lo = a > 0 ? ghost : 0;  // sample planes below voxel row a that the sub-slab starts with
-    CU(up.wait_slab(k, st));
-    if (k == S - 1)
-      if (int rc = h->rec(b200iso_handle::E_H1)) return rc;
-    if (int rc = enqueue_count(h, &pk, slabs[k].dst, b - a + 1 + lo, ny, nz, (int64_t)(slabs[k].dpitch / esz), nullptr, true)) return rc;
-    if (int rc = fetch_totals(h)) return rc;
-    const int64_t nv = h->nverts, nf = h->nfaces;
-    if (cv + nv > vcap || cf + nf > fcap) overflow = true;
-    if (!overflow && (nv > 0 || nf > 0)) {
-      DevBuf<unsigned char>& vs = (njobs & 1) ? h->vstage1 : h->vstage;
-      DevBuf<long long>& fs = (njobs & 1) ? h->fstage1 : h->fstage;
-      if (njobs >= 2) CU(down.wait_job(njobs - 2));  // this staging set's previous D2H
-      if (int rc = vs.reserve((size_t)nv * 3 * vsz + 16)) return rc;
-      if (int rc = fs.reserve((size_t)nf * 3 + 2)) return rc;
-      if (int rc = enqueue_generate(h, vs.p, nv, (int64_t*)fs.p, nf, nullptr, cv)) return rc;
-      CU(cudaEventRecord(h->slab_ev[k], st));
-      hostpipe::Downloader::Job j;
-      j.src[0] = vs.p, j.dst[0] = (unsigned char*)verts + (size_t)cv * 3 * vsz, j.bytes[0] = (size_t)nv * 3 * vsz;
-      j.src[1] = (const unsigned char*)fs.p, j.dst[1] = (unsigned char*)(faces + (size_t)cf * 3), j.bytes[1] = (size_t)nf * 3 * sizeof(int64_t);
-      j.ready = h->slab_ev[k];
-      CU(down.push(njobs++, j));
-    }
-    cv += nv, cf += nf;
-  }
+  const int rc = host_slab_pass(h, &up, verts, vcap, faces, fcap, nverts, nfaces);
   up.join();
-  CU(down.finish());  // the mesh is in the caller's arrays
-  CU(cudaStreamSynchronize(st));
-  h->counted = false;  // the handle holds the last slab only: not a state b200iso_generate may continue from
-  if (nverts) *nverts = cv;
-  if (nfaces) *nfaces = cf;
-  if (overflow) return fail(B200ISO_ECAPACITY, "mesh has %lld vertices / %lld faces, capacity is %lld / %lld", (long long)cv, (long long)cf, (long long)vcap, (long long)fcap);
-  return 0;
+  if (rc != 0 && rc != B200ISO_ECAPACITY) h->hs.clear();
+  return rc;
+}
+
+static int b200iso_extract_host_resident_impl(b200iso_handle* h, void* verts, int64_t vcap, int64_t* faces, int64_t fcap, int64_t* nverts,
+                                              int64_t* nfaces) {
+  if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  if (h->hs.empty()) return fail(B200ISO_ESTATE, "no host field resident: call b200iso_extract_host first");
+  if (vcap < 0 || fcap < 0) return fail(B200ISO_EINVAL, "negative capacity");
+  if ((vcap > 0 && !verts) || (fcap > 0 && !faces)) return fail(B200ISO_EINVAL, "output pointer is NULL");
+  DeviceGuard guard(h->device);
+  const int S = (int)h->hs.size();
+  h->begin_step();
+  CU(cudaEventRecord(h->slab_ev[S], h->stream));
+  return host_slab_pass(h, nullptr, verts, vcap, faces, fcap, nverts, nfaces);
+}
+
+int b200iso_extract_host_resident(b200iso_handle* h, void* verts, int64_t vcap, int64_t* faces, int64_t fcap, int64_t* nverts, int64_t* nfaces) {
+  try {
+    return b200iso_extract_host_resident_impl(h, verts, vcap, faces, fcap, nverts, nfaces);
+  } catch (const std::exception& e) {
+    return fail(B200ISO_ENOMEM, "b200iso_extract_host_resident: %s", e.what());
+  } catch (...) {
+    return fail(B200ISO_ENOMEM, "b200iso_extract_host_resident: unknown C++ exception");
+  }
 }
 
 int b200iso_extract_host(b200iso_handle* h, const b200iso_params* p, const void* sdf, int64_t nx, int64_t ny, int64_t nz,

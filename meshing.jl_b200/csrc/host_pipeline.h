@@ -90,10 +90,13 @@ struct Pool {
 // waiting threads sleep instead of spinning: the cores belong to the workers that are copying
 inline void nap() { std::this_thread::sleep_for(std::chrono::microseconds(20)); }
 
+// Staging threads of the upload (the download takes half as many).  The workers spend much of their time blocked in
+// cudaEventSynchronize, so more threads than cores pays: measured on the 16-vCPU B200 host at 1024^3, whole call on
+// pageable arrays: 8 threads 162 ms, 16 threads 150 ms, 24 threads 140 ms (tools/host_e2e.py, profiles/r2_host_paths.txt).
 inline int default_threads() {
   if (const char* e = getenv("B200ISO_HOST_THREADS")) return std::max(1, std::min(64, atoi(e)));
   const unsigned hw = std::thread::hardware_concurrency();
-  return (int)std::max(1u, std::min(8u, hw / 2));
+  return (int)std::max(1u, std::min(32u, hw + hw / 2));
 }
 
 // ---- field upload: x-slab k = sample planes [x0, x1) of every (y, z) row, into its own compact device array ------

@@ -445,7 +445,7 @@ def test_extract_host_equals_two_phase(pkg, oracle, monkeypatch, algo, shape, ki
     """Every slab count gives the bytes of count + generate, which the tests above pin to the oracle."""
     s = getattr(pkg.synth, kind)(shape)
     m = _method(pkg, algo, 0.0, True)
-    v0, f0 = pkg.isosurface(s, m, (0, 2), (-1, 1), (3, 4))
+    v0, f0 = pkg.api.isosurface_two_phase(s, m, (0, 2), (-1, 1), (3, 4))
     monkeypatch.setenv("B200ISO_HOST_SLABS", str(slabs))
     v1, f1 = pkg.isosurface(s, m, (0, 2), (-1, 1), (3, 4), capacity=(len(v0) + 5, len(f0) + 3))
     assert np.array_equal(f1, f0) and _bits_equal(v1, v0)
@@ -459,14 +459,16 @@ def test_extract_host_natural_slabs_and_types(pkg, oracle, algo):
     s = pkg.synth.gyroid((530, 130, 140))
     for f32 in (True, False):
         m = _method(pkg, algo, 0.05, f32)
-        v0, f0 = pkg.isosurface(s, m)
+        v0, f0 = pkg.api.isosurface_two_phase(s, m)
         v1, f1 = pkg.isosurface(s, m, capacity=(len(v0), len(f0)))
         assert v1.dtype == (np.float32 if f32 else np.float64)
         assert np.array_equal(f1, f0) and _bits_equal(v1, v0)
     s64 = pkg.synth.gyroid((150, 190, 160)).astype(np.float64) * 1.000000001
     m = _method(pkg, algo, 0.0, False)
-    v0, f0 = pkg.isosurface(s64, m)
+    v0, f0 = pkg.api.isosurface_two_phase(s64, m)
     v1, f1 = pkg.isosurface(s64, m, capacity=(len(v0), len(f0)))
+    assert np.array_equal(f1, f0) and _bits_equal(v1, v0)
+    v1, f1 = pkg.isosurface(s64, m)  # built-in guess (memo of the call above)
     assert np.array_equal(f1, f0) and _bits_equal(v1, v0)
 
 
@@ -485,8 +487,18 @@ def test_extract_host_capacity_protocol(pkg, monkeypatch):
     vb, fb = np.empty((nv // 2, 3), np.float32), np.empty((nf, 3), np.int64)
     nv2, nf2, _, fits = h.extract_host(p, a.ctypes.data, *a.shape, a.shape[0], vb.ctypes.data, len(vb), fb.ctypes.data, len(fb))
     assert (nv2, nf2, fits) == (nv, nf, False)
-    v1, f1 = pkg.isosurface(s, m, capacity=(10, 10))
+    v1, f1 = pkg.isosurface(s, m, capacity=(10, 10))  # too small: exact arrays filled from the resident slabs
     assert np.array_equal(f1, f0) and _bits_equal(v1, v0)
+    # the resident form by hand, and its state rules
+    nv3, nf3, _, fits = h.extract_host(p, a.ctypes.data, *a.shape, a.shape[0], 0, 0, 0, 0)
+    assert not fits
+    vb, fb = np.full((nv3 + 2, 3), -1, np.float32), np.full((nf3 + 2, 3), -1, np.int64)
+    assert h.extract_host_resident(vb.ctypes.data, len(vb), fb.ctypes.data, len(fb)) == (nv, nf, True)
+    assert np.array_equal(fb[:nf], f0) and _bits_equal(vb[:nv], v0) and (fb[nf:] == -1).all()
+    assert h.extract_host_resident(vb.ctypes.data, 5, fb.ctypes.data, len(fb)) == (nv, nf, False)  # still too small: still resident
+    h.count(p, a.ctypes.data, pkg.capi.HOST, *a.shape, a.shape[0])  # another host call overwrites the staging
+    with pytest.raises(pkg.capi.B200IsoError):
+        h.extract_host_resident(vb.ctypes.data, len(vb), fb.ctypes.data, len(fb))
     vb, fb = np.full((nv + 7, 3), -1, np.float32), np.full((nf + 7, 3), -1, np.int64)
     assert pkg.api.isosurface_into(a, vb, fb, m) == (nv, nf)
     assert np.array_equal(fb[:nf], f0) and _bits_equal(vb[:nv], v0)
@@ -624,7 +636,8 @@ def test_c_example_runs_through_the_c_abi(pkg, c_example):
 
 # ---- the TMA-staged classify kernel (what the 1024^3 benchmark times) against the oracle -------------------------
 TMA_SHAPES = [(16, 16, 16), (33, 20, 47), (5, 130, 37), (129, 7, 70), (12, 9, 260), (131, 9, 40), (260, 5, 1030), (2, 2, 2),
-              (127, 3, 33), (128, 4, 32), (256, 3, 513)]
+              (127, 3, 33), (128, 4, 32), (256, 3, 513),
+              (129, 20, 70), (257, 6, 40), (136, 5, 33), (137, 5, 33)]  # 128 k + 1..8 samples: the tail-column path (x-slab + halo plane)
 
 
 @pytest.fixture
