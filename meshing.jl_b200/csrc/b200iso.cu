@@ -248,24 +248,20 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
     const bool f64 = p->field_is_f64 != 0;
     const bool vec = !f64 && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(sdf_dev) & 15) == 0);
     const float* sdf_f = reinterpret_cast<const float*>(sdf_dev);
-    int nxseg = (int)((nx + iso::SP_XSEG - 1) / iso::SP_XSEG);
+    const int nxseg = (int)((nx + iso::SP_XSEG - 1) / iso::SP_XSEG);
     const int nzc = (g.W + iso::SP_ZW - 1) / iso::SP_ZW;
-    long long ntasks = (long long)nxseg * ny * nzc;
+    const long long ntasks = (long long)nxseg * ny * nzc;
     const unsigned nb = (unsigned)((ntasks + iso::SP_WARPS - 1) / iso::SP_WARPS);
     const float thr = threshold_for(p->iso, p->iso_is_f32 != 0);
     CUtensorMap tmap;
     // (measured: TMA wins on big fields -- 0.656 vs 0.694 ms at 1024^3 -- and loses a few % when the grid is under two waves)
     const bool tma_wanted = h->tma_mode == 1 || (h->tma_mode < 0 && ntasks >= 4096);
     if (vec && tma_wanted && iso::make_field_tmap(&tmap, sdf_f, nx, ny, nz, ldx)) {
-      // x-slabs with their halo plane have 128 k + 1 samples: the few columns beyond a multiple of 128 go through the
-      // tail path of the kernel (one pseudo-segment) instead of a 128-wide box each
-      const int rem = (int)(nx % iso::SP_XSEG);
-      const int ntail = (nx > iso::SP_XSEG && rem > 0 && rem <= iso::TM_TAIL_MAX) ? rem : 0;
-      if (ntail) --nxseg;  // (TMA segments; the tail tasks, one per row and z-chunk, are numbered first)
-      const long long tpr = (long long)(nxseg + (ntail ? 1 : 0)) * nzc;  // classify tasks per sample row
-      ntasks = tpr * ny;
-      // TMA-staged classify: same tasks, cp.async.bulk.tensor boxes + per-warp mbarrier pipeline; for Marching Cubes
-      // its CTAs carry counting warps that count the generate blocks while the field streams (signpack_tma.cuh)
+      // (x-slabs with their halo plane have 128 k + 1 samples: the last 128-wide segment then holds one valid column.
+      // Tail tasks for those columns were tried three ways -- lanes along z + ballot, lane per row with scalar loads,
+      // a second tensor map with 4 x * 32 y boxes -- and none beat the plain out-of-bounds box: the TMA engine does
+      // not fetch the out-of-bounds part, and a 129-plane slab is bound by its 1.7 waves of CTAs, not by that segment.)
+      const long long tpr = (long long)nxseg * nzc;  // classify tasks per sample row
       iso::CountRide cr{};
       cr.g = g;
       if (!mt && h->ride_warps > 0) {
@@ -286,7 +282,7 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
       }
       const unsigned tb = (unsigned)((ntasks + iso::TM_WARPS - 1) / iso::TM_WARPS);
       iso::signpack_tma_kernel<<<tb, (iso::TM_WARPS + (ride ? h->ride_warps : 0)) * 32, iso::TM_SMEM, st>>>(tmap, h->bits.p, g.nx, g.ny, g.nz, g.W, thr, nxseg, nzc,
-                                                                                                  ntasks, h->chain.p, nclear, cr, sdf_f, g.ldx, ntail);
+                                                                                                  ntasks, h->chain.p, nclear, cr);
       h->classify_path = B200ISO_CLASSIFY_TMA;
     } else if (vec) {
       iso::signpack_kernel<true, float><<<nb, iso::SP_WARPS * 32, 0, st>>>(sdf_f, h->bits.p, g.nx, g.ny, g.nz, g.ldx, g.W, thr, nxseg, ntasks, h->chain.p, nclear);

@@ -76,7 +76,6 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 // skips x < next_x[bi] -- the result never depends on how much was claimed here.
 // rows_done[] counts cumulatively over the steps (target = step number x tasks per row): no reset between steps;
 // cur_bi, next_x[] and the statistics word are zeroed by the scan kernel at the end of the step.
-constexpr int TM_TAIL_MAX = 8;       // up to this many columns beyond a multiple of 128 are classified by the tail path
 constexpr int TM_CNT_WARPS_MAX = 8;  // counting warps per CTA: a launch parameter (blockDim), 4 by default
 constexpr unsigned TM_CNT_BATCH = 1;  // generate blocks per claim (more per claim = longer overhang past the classify warps)
 // layout of the ride buffer (unsigned int): [0] cur_bi, [1] claimed (statistics), [32 .. 32 + nbi) next_x, then rows_done[ny]
@@ -155,7 +154,7 @@ __device__ __forceinline__ void count_ride(const uint32_t* __restrict__ bits, co
 __global__ void __launch_bounds__((TM_WARPS + TM_CNT_WARPS_MAX) * 32)
 signpack_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t* __restrict__ bits, int nx, int ny, int nz, int W,
                     float thresh, int nxseg, int nzc, long long ntasks, unsigned long long* __restrict__ clear, int nclear,
-                    const __grid_constant__ CountRide cr, const float* __restrict__ sdf, long long ldx, int ntail) {
+                    const __grid_constant__ CountRide cr) {
   extern __shared__ __align__(128) unsigned char tm_smem[];
   __shared__ __align__(8) uint64_t full[TM_WARPS][TM_STAGES];
   __shared__ uint8_t nf_s[256];
@@ -181,43 +180,12 @@ signpack_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t* __restri
   unsigned char* base = tm_smem + (128 - (smem_u32(tm_smem) & 127)) % 128 + (size_t)wib * TM_SMEM_PER_WARP;
   float* box = reinterpret_cast<float*>(base);                                                      // [TM_STAGES][TM_BZ][128]
   uint32_t* wstage = reinterpret_cast<uint32_t*>(base + (size_t)TM_STAGES * TM_BOX_FLOATS * 4);      // [SP_ZW][128]
-  // Task order: the (cheap) tail-column tasks of all rows first, then the TMA tasks y-major: rows complete one after
-  // the other while the kernel runs (the counting warps follow them).  nxseg counts the TMA segments only.
-  const long long ntail_tasks = ntail > 0 ? (long long)ny * nzc : 0;
-  const bool tail = task < ntail_tasks;
-  const long long tm = tail ? task : task - ntail_tasks;
-  const int xseg = tail ? nxseg : (int)(tm % nxseg);
-  const long long t2 = tail ? tm : tm / nxseg;
+  // y-major task order: rows complete one after the other while the kernel runs (the counting warps follow them)
+  const int xseg = (int)(task % nxseg);
+  const long long t2 = task / nxseg;
   const int zc = (int)(t2 % nzc);
   const int y = (int)(t2 / nzc);
   const int x0 = xseg * SP_XSEG, z0 = zc * SP_ZW * 32;
-  if (tail) {
-    // ---- tail columns: nx = 128 k + ntail with ntail <= TM_TAIL_MAX (an x-slab with its halo plane: 129, 257 samples).
-    // A 128-wide TMA box for one valid column would double the classify work of a 129-plane slab; instead the lanes
-    // run along z: lane l loads sample (x, y, 32 w + l), one ballot is the z-packed word w of the column.
-    const long long plane = ldx * ny;
-    for (int c = 0; c < ntail; ++c) {
-      const int x = x0 + c;
-      const float* p = sdf + x + ldx * (long long)y + plane * (long long)(z0 + lane);
-      uint32_t mine = 0;
-#pragma unroll
-      for (int w = 0; w < SP_ZW; ++w) {
-        const int z = z0 + w * 32 + lane;
-        const float v = z < nz ? ldg_stream_f1(p + plane * (long long)(w * 32)) : __int_as_float(0x7fc00000);
-        const uint32_t word = __ballot_sync(0xffffffffu, v < thresh);
-        if (lane == w) mine = word;
-      }
-      const int wofs = zc * SP_ZW;
-      if (lane < SP_ZW && wofs + lane < W) bits[((long long)x * ny + y) * W + wofs + lane] = mine;
-    }
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) {
-      if (cr.nbi > 0) atomicAdd(cr.rows_done + y, 1u);
-      atomicAdd(&cta_prog, SP_ZW);
-    }
-    return;
-  }
   // boxes of this task that contain at least one valid z-plane
   const int nbox = min(TM_BOXES, (nz - z0 + TM_BZ - 1) / TM_BZ);
 

@@ -637,7 +637,7 @@ def test_c_example_runs_through_the_c_abi(pkg, c_example):
 # ---- the TMA-staged classify kernel (what the 1024^3 benchmark times) against the oracle -------------------------
 TMA_SHAPES = [(16, 16, 16), (33, 20, 47), (5, 130, 37), (129, 7, 70), (12, 9, 260), (131, 9, 40), (260, 5, 1030), (2, 2, 2),
               (127, 3, 33), (128, 4, 32), (256, 3, 513),
-              (129, 20, 70), (257, 6, 40), (136, 5, 33), (137, 5, 33)]  # 128 k + 1..8 samples: the tail-column path (x-slab + halo plane)
+              (129, 20, 70), (257, 6, 40), (132, 40, 33), (130, 70, 600), (136, 5, 33)]  # 128 k + 1..8 samples: x-slabs with their halo plane (a nearly empty last x-segment)
 
 
 @pytest.fixture

@@ -7,7 +7,12 @@ from __graft_entry__ import load_package
 pkg = load_package()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 kind = sys.argv[2] if len(sys.argv) > 2 else "gyroid"
-t = pkg.synth.gyroid_torch(n, "cuda") if kind == "gyroid" else pkg.synth.multisphere_torus((n // 4 + 1, n, n), x_slice=None, xp=torch, device="cuda")
+if kind == "gyroid":
+    t = pkg.synth.gyroid_torch(n, "cuda")
+elif kind == "gyroid129":  # one rank's slab of the 1024^3 volume split over 8 GPUs
+    t = pkg.synth.gyroid_torch(n, "cuda", x_slice=(0, n // 8 + 1), ldx=n // 8 + 4)
+else:  # rank 3's slab of the 2048^3 multi-sphere/torus volume split over 8 GPUs
+    t = pkg.synth.multisphere_torus((n, n, n), x_slice=(3 * n // 8, 4 * n // 8 + 1), xp=torch, device="cuda", ldx=n // 8 + 4)
 nx = t.shape[0]
 p = pkg.api.make_params(pkg.MarchingCubes(iso=pkg.Float32(0)))
 h = pkg.capi.Handle(0)
