@@ -95,7 +95,9 @@ inline void nap() { std::this_thread::sleep_for(std::chrono::microseconds(20)); 
 // pageable arrays: 8 threads 162 ms, 16 threads 150 ms, 24 threads 140 ms (tools/host_e2e.py, profiles/r2_host_paths.txt).
 inline int default_threads() {
   if (const char* e = getenv("B200ISO_HOST_THREADS")) return std::max(1, std::min(64, atoi(e)));
-  const unsigned hw = std::thread::hardware_concurrency();
+  unsigned hw = std::thread::hardware_concurrency();
+  // one process per GPU on a shared host (torchrun exports LOCAL_WORLD_SIZE): the ranks share the cores
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) hw = std::max(2u, hw / (unsigned)std::max(1, atoi(e)));
   return (int)std::max(1u, std::min(32u, hw + hw / 2));
 }
 
