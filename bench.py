@@ -160,7 +160,9 @@ def ncu_traffic(kernel, workload):
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(workload, {}).get(kernel)
+            tab = json.load(open(p)).get(workload, {})
+            vals = [tab.get(k) for k in kernel.split("+")]  # (a stage of two kernels: the sum)
+            return None if any(v is None for v in vals) else float(sum(vals))
         except Exception:
             return None
     return None

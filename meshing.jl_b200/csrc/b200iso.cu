@@ -264,7 +264,9 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
       const long long tpr = (long long)nxseg * nzc;  // classify tasks per sample row
       iso::CountRide cr{};
       cr.g = g;
-      if (!mt && h->ride_warps > 0) {
+      // (only when the classify kernel runs for many waves of CTAs: on a 129-plane slab -- 4096 tasks, 3.5 waves -- the
+      // rows complete too late for the riding warps to get anything done, and they only cost: 0.139 vs 0.122 ms)
+      if (!mt && h->ride_warps > 0 && ntasks >= 8192) {
         const long long nbi = g.blocks_per_row;
         const size_t words = (size_t)iso::RIDE_HDR + (size_t)nbi + (size_t)ny;
         if (int rc = h->ride.reserve(words)) return rc;

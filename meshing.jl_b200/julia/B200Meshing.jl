@@ -16,7 +16,7 @@
 module B200Meshing
 
 export isosurface, MarchingCubes, MarchingTetrahedra
-# (B200Meshing.isosurface_sized is the one-shot host form; not exported, the reference has no such name)
+# (B200Meshing.isosurface_two_phase is the count -> allocate -> generate form; not exported, the reference has no such name)
 
 const libb200iso = get(ENV, "B200ISO_LIB", joinpath(@__DIR__, "..", "lib", "libb200iso.so"))
 
@@ -53,15 +53,26 @@ const B200ISO_ECAPACITY = Cint(-5)
 last_error() = unsafe_string(ccall((:b200iso_last_error, libb200iso), Cstring, ()))
 check(rc) = rc == 0 ? nothing : error("b200iso error $rc: $(last_error())")
 
-# one handle per thread (a handle is not thread-safe); created lazily on device B200ISO_DEVICE (default 0)
-const handles = Dict{Int,Ptr{Cvoid}}()
-const handles_lock = ReentrantLock()   # the Dict itself is shared between threads
-function handle()
-    lock(handles_lock) do
-        get!(handles, Threads.threadid()) do
-            h = Ref{Ptr{Cvoid}}(C_NULL)
-            check(ccall((:b200iso_create, libb200iso), Cint, (Ref{Ptr{Cvoid}}, Cint), h, parse(Cint, get(ENV, "B200ISO_DEVICE", "0"))))
-            h[]
+# A handle is not thread-safe and a call is a multi-step conversation with it (extract -> maybe fetch), so handles are
+# checked out of a pool for the duration of ONE isosurface call and returned afterwards.  (Keying them by
+# Threads.threadid() is not safe: a Julia task may migrate between threads in the middle of a call.)
+const handle_pool = Ptr{Cvoid}[]
+const handle_pool_lock = ReentrantLock()
+function new_handle()
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:b200iso_create, libb200iso), Cint, (Ref{Ptr{Cvoid}}, Cint), h, parse(Cint, get(ENV, "B200ISO_DEVICE", "0"))))
+    h[]
+end
+function with_handle(f)
+    h = lock(handle_pool_lock) do
+        isempty(handle_pool) ? C_NULL : pop!(handle_pool)
+    end
+    h == C_NULL && (h = new_handle())
+    try
+        return f(h)
+    finally
+        lock(handle_pool_lock) do
+            push!(handle_pool, h)
         end
     end
 end
@@ -81,8 +92,16 @@ range_kind(::Type{Float32}) = Int32(1)
 range_kind(::Type{Float64}) = Int32(2)
 range_kind(T) = throw(ArgumentError("unsupported range element type $T on the B200 path"))
 
+# The vertex type follows eltype(first(X)) only (src/marching_cubes.jl:31), the coordinates follow
+# LinRange(first(X), last(X), n), i.e. the promotion of both endpoints (:36-38):
+#   first is Float64 -> 2; else promote(first, last) is Float32 -> 1; else (Int/Int, Int/Float64, Float32/Float64) -> 0
+function axis_kind(R)
+    a, b = range_kind(typeof(first(R))), range_kind(typeof(last(R)))
+    a == 2 ? Int32(2) : ((a != 2 && b != 2 && (a == 1 || b == 1)) ? Int32(1) : Int32(0))
+end
+
 function params(method, X, Y, Z, field_is_f64::Bool)
-    kx, ky, kz = range_kind(typeof(first(X))), range_kind(typeof(first(Y))), range_kind(typeof(first(Z)))
+    kx, ky, kz = axis_kind(X), axis_kind(Y), axis_kind(Z)
     kx == ky == kz || throw(ArgumentError("X, Y, Z must share an element type on the B200 path"))
     iso, isf = scalar_kind(method.iso)
     if method isa MarchingCubes
@@ -97,49 +116,73 @@ end
 vertex_eltype(p::Params) =
     (p.field_is_f64 != 0 || p.iso_is_f32 == 0 || p.range_kind == 2 || (p.algo == B200ISO_MT && p.eps_is_f32 == 0)) ? Float64 : Float32
 
+# Capacity guess for the one-shot call: the totals of the previous call with the same shape and method plus 1/8, else
+# an estimate from the surface area an isosurface of this grid typically has (the 1024^3 gyroid: 38.7 n^2 MC vertices,
+# 19.3 n^2 faces; MT 27.7 n^2 / 55.2 n^2).  Over-allocation is free: untouched pages of an `undef` Vector are never
+# backed by memory, and `resize!` to a smaller length does not copy.
+const capacity_memo = Dict{Tuple{NTuple{3,Int},DataType,Int32},NTuple{2,Int}}()
+const capacity_memo_lock = ReentrantLock()
+function capacity_guess(key, dims, algo)
+    m = lock(() -> get(capacity_memo, key, nothing), capacity_memo_lock)
+    m === nothing || return (m[1] + m[1] ÷ 8 + 1024, m[2] + m[2] ÷ 8 + 1024)
+    nx, ny, nz = max.(dims .- 1, 0)
+    area = (nx * ny + ny * nz + nx * nz) / 3
+    nvox = nx * ny * nz
+    algo == B200ISO_MC ? (Int(floor(min(64area, 12nvox))) + 1024, Int(floor(min(32area, 5nvox))) + 1024) :
+                         (Int(floor(min(48area, 7nvox))) + 1024, Int(floor(min(96area, 12nvox))) + 1024)
+end
+
+# The drop-in body: ONE b200iso_extract_host into arrays sized by the guess -- the mesh streams out of the GPU while the
+# field still streams in (x-slab pipeline) -- then trim.  If the guess was short (B200ISO_ECAPACITY, exact totals
+# returned) the mesh is fetched into exact arrays from the slabs still resident on the device
+# (b200iso_extract_host_resident): the field is uploaded once in every case.
 function _isosurface(sdf::Union{Array{Float32,3},Array{Float64,3}}, method, X, Y, Z)
     nx, ny, nz = size(sdf)
     p = Ref(params(method, X, Y, Z, eltype(sdf) === Float64))
-    h = handle()
-    nv, nf, f64 = Ref{Int64}(0), Ref{Int64}(0), Ref{Cint}(0)
-    GC.@preserve sdf begin
-        check(ccall((:b200iso_count, libb200iso), Cint,
-                    (Ptr{Cvoid}, Ref{Params}, Ptr{Cvoid}, Cint, Int64, Int64, Int64, Int64, Ref{Int64}, Ref{Int64}, Ref{Cint}),
-                    h, p, pointer(sdf), B200ISO_HOST, nx, ny, nz, nx, nv, nf, f64))
-    end
     VT = vertex_eltype(p[])
-    @assert (f64[] != 0) == (VT === Float64)
-    vts = Vector{NTuple{3,VT}}(undef, nv[])
-    fcs = Vector{NTuple{3,Int}}(undef, nf[])
-    GC.@preserve vts fcs begin
-        check(ccall((:b200iso_generate, libb200iso), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Cint, Int64),
-                    h, pointer(vts), pointer(fcs), B200ISO_HOST, 0))
-    end
-    vts, fcs
-end
-
-# One-shot form for callers that can guess (or remember) the mesh size: b200iso_extract_host pipelines H2D, kernels
-# and D2H over x-slabs.  `capacity` = (max vertices, max faces); a short guess costs one exact re-run.
-function isosurface_sized(sdf::Union{Array{Float32,3},Array{Float64,3}}, method::Union{MarchingCubes,MarchingTetrahedra},
-                          X=-1:1, Y=-1:1, Z=-1:1; capacity::NTuple{2,Int})
-    nx, ny, nz = size(sdf)
-    p = Ref(params(method, X, Y, Z, eltype(sdf) === Float64))
-    h = handle()
-    VT = vertex_eltype(p[])
+    key = (size(sdf), eltype(sdf), p[].algo)
+    vcap, fcap = capacity_guess(key, size(sdf), p[].algo)
     nv, nf, f64 = Ref{Int64}(0), Ref{Int64}(0), Ref{Cint}(0)
-    vcap, fcap = capacity
-    for _ in 1:2
-        vts = Vector{NTuple{3,VT}}(undef, vcap)
-        fcs = Vector{NTuple{3,Int}}(undef, fcap)
+    vts = Vector{NTuple{3,VT}}(undef, vcap)
+    fcs = Vector{NTuple{3,Int}}(undef, fcap)
+    with_handle() do h
         rc = GC.@preserve sdf vts fcs ccall((:b200iso_extract_host, libb200iso), Cint,
             (Ptr{Cvoid}, Ref{Params}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ptr{Cvoid}, Int64, Ptr{Int64}, Int64,
              Ref{Int64}, Ref{Int64}, Ref{Cint}),
             h, p, pointer(sdf), nx, ny, nz, nx, pointer(vts), vcap, pointer(fcs), fcap, nv, nf, f64)
-        rc == 0 && return resize!(vts, nv[]), resize!(fcs, nf[])
-        rc == B200ISO_ECAPACITY || check(rc)
-        vcap, fcap = nv[], nf[]
+        if rc == B200ISO_ECAPACITY
+            vts = Vector{NTuple{3,VT}}(undef, nv[])
+            fcs = Vector{NTuple{3,Int}}(undef, nf[])
+            GC.@preserve vts fcs check(ccall((:b200iso_extract_host_resident, libb200iso), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Int64}, Int64, Ref{Int64}, Ref{Int64}),
+                h, pointer(vts), nv[], pointer(fcs), nf[], nv, nf))
+        else
+            check(rc)
+        end
     end
-    error("b200iso_extract_host: capacity still too small after an exact re-run")
+    @assert (f64[] != 0) == (VT === Float64)
+    lock(() -> (capacity_memo[key] = (Int(nv[]), Int(nf[]))), capacity_memo_lock)
+    resize!(vts, nv[]), resize!(fcs, nf[])
+end
+
+# The two-phase pair (count: the caller learns the sizes; generate: into exact arrays) for callers that cannot
+# over-allocate; no overlap between the upload and the download.
+function isosurface_two_phase(sdf::Union{Array{Float32,3},Array{Float64,3}}, method::Union{MarchingCubes,MarchingTetrahedra},
+                              X=-1:1, Y=-1:1, Z=-1:1)
+    nx, ny, nz = size(sdf)
+    p = Ref(params(method, X, Y, Z, eltype(sdf) === Float64))
+    VT = vertex_eltype(p[])
+    nv, nf, f64 = Ref{Int64}(0), Ref{Int64}(0), Ref{Cint}(0)
+    with_handle() do h
+        GC.@preserve sdf check(ccall((:b200iso_count, libb200iso), Cint,
+            (Ptr{Cvoid}, Ref{Params}, Ptr{Cvoid}, Cint, Int64, Int64, Int64, Int64, Ref{Int64}, Ref{Int64}, Ref{Cint}),
+            h, p, pointer(sdf), B200ISO_HOST, nx, ny, nz, nx, nv, nf, f64))
+        vts = Vector{NTuple{3,VT}}(undef, nv[])
+        fcs = Vector{NTuple{3,Int}}(undef, nf[])
+        GC.@preserve vts fcs check(ccall((:b200iso_generate, libb200iso), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Cint, Int64),
+            h, pointer(vts), pointer(fcs), B200ISO_HOST, 0))
+        vts, fcs
+    end
 end
 
 # same positional signature and defaults as the reference
