@@ -100,7 +100,7 @@ struct b200iso_handle {
   // scan state, cleared by block 0 of the classify kernel: [0] = ticket, [2 ..) = look-back chain of the scan blocks
   DevBuf<unsigned long long> chain;
   DevBuf<unsigned long long> status;  // MT: inclusive (vertex, face) prefix of every generate block (FLAG_INC | value)
-  DevBuf<uint32_t> recs, nrecs;       // MC: active-voxel records of every generate block (REC_CAP each) and their number
+  DevBuf<uint32_t> recs, nrecs;       // active-voxel records of every generate block (REC_CAP each) and their number
   DevBuf<unsigned long long> woff;    // MC: exclusive (vertex, face) prefix of every generate block; MT: raw block totals
   DevBuf<double> coords;
   DevBuf<uint8_t> cases;             // b200iso_case_indices(HOST): device scratch, kept across calls
@@ -230,10 +230,9 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
   if (mt) {
     if (int rc = h->status.reserve((size_t)h->nblocks * 2)) return rc;
     if (int rc = h->celloff.reserve(nbits)) return rc;
-  } else {
-    if (int rc = h->recs.reserve((size_t)h->nblocks * iso::REC_CAP + 2)) return rc;
-    if (int rc = h->nrecs.reserve((size_t)h->nblocks)) return rc;
   }
+  if (int rc = h->recs.reserve((size_t)h->nblocks * iso::REC_CAP + 2)) return rc;
+  if (int rc = h->nrecs.reserve((size_t)h->nblocks)) return rc;
   if (int rc = h->coords.reserve((size_t)(nx + ny + nz))) return rc;
   unsigned int* ticket = reinterpret_cast<unsigned int*>(h->chain.p);
   unsigned long long* chain = h->chain.p + 2;
@@ -315,7 +314,7 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
     iso::mc_scan_chunks_kernel<<<(unsigned)nsb, iso::SC_THREADS, 0, st>>>(h->woff.p, h->nblocks, chain, ticket, nsb, h->totals_dev, totals_out,
                                                                           ride ? h->ride.p : nullptr, ride ? iso::RIDE_HDR + g.blocks_per_row : 0);
   } else {
-    iso::mt_count_kernel<<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->celloff.p, h->woff.p);
+    iso::mt_count_kernel<<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->celloff.p, h->woff.p, h->recs.p, h->nrecs.p);
     CU(cudaGetLastError());
     iso::mt_scan_blocks_kernel<<<(unsigned)nsb, iso::SC_THREADS, 0, st>>>(h->woff.p, h->nblocks, h->status.p, chain, ticket, nsb,
                                                                           g.ghost ? (long long)g.blocks_per_row - 1 : -1LL, ghost_words, h->totals_dev, totals_out);

@@ -16,7 +16,8 @@
 namespace iso {
 
 __global__ void __launch_bounds__(CB_THREADS)
-mt_count_kernel(const uint32_t* __restrict__ bits, Grid g, uint32_t* __restrict__ celloff, unsigned long long* __restrict__ raw) {
+mt_count_kernel(const uint32_t* __restrict__ bits, Grid g, uint32_t* __restrict__ celloff, unsigned long long* __restrict__ raw,
+                uint32_t* __restrict__ recs, uint32_t* __restrict__ nrecs) {
   __shared__ uint8_t nf_s[256];
   __shared__ uint32_t s_w[CB_THREADS / 32];
   __shared__ uint32_t red_v[CB_THREADS / 32], red_f[CB_THREADS / 32];
@@ -26,25 +27,38 @@ mt_count_kernel(const uint32_t* __restrict__ bits, Grid g, uint32_t* __restrict_
   const TMap tm = thread_map(g, b);
   uint32_t nv = 0, nf = 0;
   uint32_t cv[4] = {0, 0, 0, 0};
-  if (tm.live) {
-    Quad q;
-    if (load_quad(bits, g, tm.x, tm.y, tm.zq, q)) {
-      const int fxy = ((tm.x + g.xoff) == 0 ? 1 : 0) | (tm.y == 0 ? 2 : 0);  // low-boundary flags use GLOBAL x
+  // Like the Marching Cubes count, this one leaves the block's active-voxel records for generate (scan order, 4 bytes:
+  // case | voxel-in-quad-cell << 8 | quad-cell-in-block << 15, up to REC_CAP per block) and their number.
+  Quad q;
+  uint32_t mm4[4] = {0, 0, 0, 0}, na = 0;
+  if (tm.live && load_quad(bits, g, tm.x, tm.y, tm.zq, q)) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint32_t mm = active_mask(q, i);
-        if (mm) {
-          cv[i] = mt_owned_masked(q, i, q.vm[i], fxy, tm.zq == 0 && i == 0);
-          nv += cv[i];
-          while (mm) {
-            const int k = __ffs(mm) - 1;
-            mm &= mm - 1;
-            nf += nf_s[case_of<1>(q, i, k)];
-          }
+    for (int i = 0; i < 4; ++i) mm4[i] = active_mask(q, i), na += __popc(mm4[i]);
+  }
+  uint32_t blk_na;
+  uint32_t pos = block_excl_scan_u32(na, s_w, blk_na);
+  if (na) {
+    const int fxy = ((tm.x + g.xoff) == 0 ? 1 : 0) | (tm.y == 0 ? 2 : 0);  // low-boundary flags use GLOBAL x
+    uint32_t* rec = recs + (unsigned long long)b * REC_CAP;
+    const uint32_t qtag = (uint32_t)threadIdx.x << 15;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t mm = mm4[i];
+      if (mm) {
+        cv[i] = mt_owned_masked(q, i, q.vm[i], fxy, tm.zq == 0 && i == 0);
+        nv += cv[i];
+        while (mm) {
+          const int k = __ffs(mm) - 1;
+          mm &= mm - 1;
+          const uint32_t c = case_of<1>(q, i, k);
+          nf += nf_s[c];
+          if (pos < (uint32_t)REC_CAP) rec[pos] = c | ((uint32_t)(i * 32 + k) << 8) | qtag;
+          ++pos;
         }
       }
     }
   }
+  if (threadIdx.x == 0) nrecs[b] = blk_na;
   {
     // in-block exclusive vertex prefix of every cell (thread order == scan order)
     uint32_t tot;

@@ -164,14 +164,18 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
 #endif
   for (int i = tid; i < 20; i += CB_THREADS) einfo_s[i] = ISO_MT_EDGE_INFO[i], slot_s[i] = ISO_MT_OWN_SLOT[i];
   for (int i = tid; i < 160; i += CB_THREADS) eshift_s[i] = ISO_MT_EDGE_SHIFT[i];
-  // ---- A: active voxels per thread, exclusive scan (thread order == scan order) ----
-  uint32_t tna;
-  {
+  // The count left the block's active-voxel records (scan order) unless there are more than REC_CAP of them: then
+  // (dense fields) this block derives them from the bit-field itself (A + B1a).
+  const uint32_t nrec = __ldg(a.nrecs + b);
+  const bool from_recs = nrec <= (uint32_t)REC_CAP;  // (uniform over the block)
+  const uint32_t q_lo = (b - (unsigned)x * (unsigned)g.blocks_per_row) * CB_THREADS;  // first quad-cell of the block in its x-row
+  uint32_t tna = 0, my_a0 = 0, blk_na = nrec;
+  if (!from_recs) {
+    // ---- A: active voxels per thread, exclusive scan (thread order == scan order) ----
     Quad qc;  // (not kept: the MT kernel is register-bound, the push reloads the quad-cell through L1)
     tna = count_active(a.bits, g, tm, qc);
+    my_a0 = block_excl_scan_u32(tna, s_w, blk_na);
   }
-  uint32_t blk_na;
-  const uint32_t my_a0 = block_excl_scan_u32(tna, s_w, blk_na);
   if (blk_na == 0) return;
 
   unsigned long long bv = 0, bf = 0;
@@ -204,7 +208,13 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
     const uint32_t hi = min(lo + (uint32_t)MTG_NB, blk_na);
     const uint32_t cnt = hi - lo;
     // ---- B1a: records (position, case) of the window's voxels, in scan order ----
-    if (tna && my_a0 < hi && my_a0 + tna > lo) {
+    if (from_recs) {
+      if ((uint32_t)tid < cnt) {  // the count's record: case | voxel-in-quad-cell << 8 | quad-cell-in-block << 15
+        const uint32_t wd = __ldg(a.recs + (unsigned long long)b * REC_CAP + lo + tid);
+        const uint32_t qr = q_lo + (wd >> 15), y = qr / (uint32_t)g.Wq, zq = qr - y * (uint32_t)g.Wq;
+        rec_yc[tid] = make_uint2(y | ((zq * 128u + ((wd >> 8) & 127u)) << 16), wd & 0xffu);
+      }
+    } else if (tna && my_a0 < hi && my_a0 + tna > lo) {
       Quad qp;
       load_quad(a.bits, g, tm.x, tm.y, tm.zq, qp);
       push_records<1>(qp, tm, my_a0, lo, hi, rec_yc, 1);
