@@ -198,6 +198,35 @@ int b200iso_extract_host(b200iso_handle* h, const b200iso_params* p, const void*
 int b200iso_extract_host_resident(b200iso_handle* h, void* verts, int64_t vcap, int64_t* faces, int64_t fcap,
                                   int64_t* nverts, int64_t* nfaces);
 
+/* ---- mesh consumers: what callers run next on the mesh (not part of Meshing.jl v0.7.0) ------------
+ * b200iso_vertex_normals_async: unit normals of `nverts` vertices (device, Float32 or Float64 triples) from the gradient
+ *                       of the field (device, same conventions as count: nx*ny*nz samples, leading dimension ldx; a
+ *                       slab with x_offset / nx_global): trilinear blend of central differences, pointing towards
+ *                       increasing field values (outwards for "negative inside"); float[3*nverts]; (0,0,0) where the
+ *                       gradient vanishes.  Works for Marching Cubes and Marching Tetrahedra vertices alike.
+ * b200iso_vertex_keys_async: after a Marching Cubes count, the grid-edge key of every vertex in output order
+ *                       (3 * linear index of the edge's lower end node in the whole volume + axis), Int64[kcap].
+ *                       Meshing.jl's Marching Cubes repeats the vertex of an edge in every voxel that touches it
+ *                       (src/algorithmtypes.jl:18-19: "vertices may be repeated"); equal keys <=> same geometric vertex.
+ * b200iso_weld        : the indexed (welded) form of a Marching Cubes mesh: keeps the first occurrence of every key in
+ *                       output order, writes the kept vertices to verts_out_dev (capacity nverts) and the renumbered
+ *                       faces (1-based into the welded vertices) to faces_out_dev (3*nfaces); `vertex_base` is what the
+ *                       faces' indices carry on top of 1-based local ones (0 for an unsharded mesh).  Returns the
+ *                       number of welded vertices.  Synchronous; all pointers are device pointers.
+ * b200iso_write_ply / b200iso_write_stl: binary little-endian PLY (optional per-vertex normals) / binary STL of a mesh
+ *                       in HOST memory (1-based Int64 faces as returned by the extraction). */
+int b200iso_vertex_normals_async(b200iso_handle* h, const b200iso_params* p, const void* sdf_dev, int64_t nx, int64_t ny,
+                                 int64_t nz, int64_t ldx, const void* verts_dev, int64_t nverts, int vert_is_f64,
+                                 float* normals_dev);
+int b200iso_vertex_keys_async(b200iso_handle* h, int64_t* keys_dev, int64_t kcap);
+int b200iso_weld(b200iso_handle* h, const int64_t* keys_dev, const void* verts_dev, int64_t nverts, int vert_is_f64,
+                 const int64_t* faces_dev, int64_t nfaces, int64_t vertex_base, void* verts_out_dev,
+                 int64_t* faces_out_dev, int64_t* nwelded);
+int b200iso_write_ply(const char* path, const void* verts, int64_t nverts, int vert_is_f64, const float* normals,
+                      const int64_t* faces, int64_t nfaces);
+int b200iso_write_stl(const char* path, const void* verts, int64_t nverts, int vert_is_f64, const int64_t* faces,
+                      int64_t nfaces);
+
 /* ---- parity / introspection ----------------------------------------------------------------------------
  * Per-voxel case index (_get_cubeindex, src/common.jl:10-20; corner order of the counted algo) for the
  * last counted field, (nx-1)(ny-1)(nz-1) bytes in scan-rank order ((x*(ny-1)+y)*(nz-1)+z). */

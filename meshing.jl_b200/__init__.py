@@ -12,3 +12,4 @@ from .api import MarchingCubes, MarchingTetrahedra, isosurface, Float32, Float64
 from . import capi  # noqa: F401
 from . import sharding  # noqa: F401
 from . import api  # noqa: F401
+from . import mesh  # noqa: F401

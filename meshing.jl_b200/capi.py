@@ -86,6 +86,11 @@ def load():
     L.b200iso_ride_claimed.argtypes = [vp]
     L.b200iso_ride_claimed.restype = i64
     L.b200iso_set_peer_timeout.argtypes = [vp, ctypes.c_double]
+    L.b200iso_vertex_normals_async.argtypes = [vp, pp, vp, i64, i64, i64, i64, vp, i64, ci, vp]
+    L.b200iso_vertex_keys_async.argtypes = [vp, vp, i64]
+    L.b200iso_weld.argtypes = [vp, vp, vp, i64, ci, vp, i64, i64, vp, vp, pi64]
+    L.b200iso_write_ply.argtypes = [ctypes.c_char_p, vp, i64, ci, vp, vp, i64]
+    L.b200iso_write_stl.argtypes = [ctypes.c_char_p, vp, i64, ci, vp, i64]
     L.b200iso_case_indices.argtypes = [vp, vp, ci]
     L.b200iso_enable_timing.argtypes = [vp, ci]
     L.b200iso_timings.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ci]
@@ -208,6 +213,21 @@ class Handle:
         _check(self.L.b200iso_add_vertex_base_async(self.h, ctypes.c_void_p(faces_dev_ptr), fcap,
                                                     ctypes.c_void_p(totals_dev_ptr), ctypes.c_void_p(vertex_base_dev_ptr)))
 
+    def vertex_normals_async(self, params, sdf_dev_ptr, nx, ny, nz, ldx, verts_dev_ptr, nverts, vert_is_f64, normals_dev_ptr):
+        _check(self.L.b200iso_vertex_normals_async(self.h, ctypes.byref(params), ctypes.c_void_p(sdf_dev_ptr), nx, ny, nz, ldx,
+                                                   ctypes.c_void_p(verts_dev_ptr), nverts, int(vert_is_f64), ctypes.c_void_p(normals_dev_ptr)))
+
+    def vertex_keys_async(self, keys_dev_ptr, kcap):
+        _check(self.L.b200iso_vertex_keys_async(self.h, ctypes.c_void_p(keys_dev_ptr), kcap))
+
+    def weld(self, keys_dev_ptr, verts_dev_ptr, nverts, vert_is_f64, faces_dev_ptr, nfaces, vertex_base, verts_out_dev_ptr, faces_out_dev_ptr):
+        """-> number of welded vertices"""
+        n = ctypes.c_int64()
+        _check(self.L.b200iso_weld(self.h, ctypes.c_void_p(keys_dev_ptr), ctypes.c_void_p(verts_dev_ptr), nverts, int(vert_is_f64),
+                                   ctypes.c_void_p(faces_dev_ptr or 0), nfaces, vertex_base, ctypes.c_void_p(verts_out_dev_ptr),
+                                   ctypes.c_void_p(faces_out_dev_ptr or 0), ctypes.byref(n)))
+        return n.value
+
     def totals(self):
         nv, nf, f64 = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()
         _check(self.L.b200iso_totals(self.h, ctypes.byref(nv), ctypes.byref(nf), ctypes.byref(f64)))
@@ -226,3 +246,12 @@ class Handle:
 
     def launch_count(self):
         return self.L.b200iso_launch_count(self.h)
+
+
+def write_ply(path, verts_ptr, nverts, vert_is_f64, normals_ptr, faces_ptr, nfaces):
+    _check(load().b200iso_write_ply(os.fsencode(path), ctypes.c_void_p(verts_ptr or 0), nverts, int(vert_is_f64), ctypes.c_void_p(normals_ptr or 0),
+                                    ctypes.c_void_p(faces_ptr or 0), nfaces))
+
+
+def write_stl(path, verts_ptr, nverts, vert_is_f64, faces_ptr, nfaces):
+    _check(load().b200iso_write_stl(os.fsencode(path), ctypes.c_void_p(verts_ptr or 0), nverts, int(vert_is_f64), ctypes.c_void_p(faces_ptr or 0), nfaces))

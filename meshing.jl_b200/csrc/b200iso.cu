@@ -22,6 +22,8 @@
 #include "count_kernel.cuh"
 #include "signpack_tma.cuh"
 #include "host_pipeline.h"
+#include "mesh_consumers.cuh"
+#include <cub/device/device_scan.cuh>
 
 namespace {
 
@@ -104,6 +106,9 @@ struct b200iso_handle {
   DevBuf<unsigned long long> woff;    // MC: exclusive (vertex, face) prefix of every generate block; MT: raw block totals
   DevBuf<double> coords;
   DevBuf<uint8_t> cases;             // b200iso_case_indices(HOST): device scratch, kept across calls
+  DevBuf<unsigned long long> weld_tab;  // mesh consumers: hash table (keys | representatives), slots, flags, new indices, cub scratch
+  DevBuf<unsigned int> weld_u32;
+  DevBuf<unsigned char> weld_tmp;
   // counting warps inside the TMA classify kernel (signpack_tma.cuh): header | next_x[nbi] | rows_done[ny]
   DevBuf<unsigned int> ride;
   long long ride_ny = -1, ride_tpr = -1, ride_nbi = -1;  // shape the cumulative row counters belong to
@@ -439,6 +444,7 @@ int b200iso_destroy(b200iso_handle* h) {
   h->pool.release();
   h->bits.release(), h->celloff.release(), h->woff.release(), h->chain.release(), h->status.release(), h->coords.release(), h->field.release(), h->vstage.release(), h->fstage.release();
   h->cases.release(), h->ride.release(), h->recs.release(), h->nrecs.release();
+  h->weld_tab.release(), h->weld_u32.release(), h->weld_tmp.release();
   if (h->totals_dev) cudaFree(h->totals_dev);
   if (h->totals_host) cudaFreeHost(h->totals_host);
   if (h->ev) {
@@ -892,6 +898,185 @@ int b200iso_case_indices(b200iso_handle* h, uint8_t* out, int mem) {
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   if (e != cudaSuccess) return fail(B200ISO_ECUDA, "case_indices: %s", cudaGetErrorString(e));
   return 0;
+}
+
+// ---- mesh consumers (csrc/mesh_consumers.cuh) ---------------------------------------------------------
+int b200iso_vertex_normals_async(b200iso_handle* h, const b200iso_params* p, const void* sdf_dev, int64_t nx, int64_t ny, int64_t nz,
+                                 int64_t ldx, const void* verts_dev, int64_t nverts, int vert_is_f64, float* normals_dev) {
+  if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  if (int rc = check_params(p, nx, ny, nz, ldx)) return rc;
+  if (nverts < 0 || (nverts > 0 && (!sdf_dev || !verts_dev || !normals_dev))) return fail(B200ISO_EINVAL, "NULL argument");
+  if (nx < 1 || ny < 1 || nz < 1) return nverts == 0 ? 0 : fail(B200ISO_EINVAL, "empty field");
+  if (nverts == 0) return 0;
+  DeviceGuard guard(h->device);
+  iso::NormalArgs a{};
+  a.sdf = sdf_dev, a.field_is_f64 = p->field_is_f64, a.nx = (int)nx, a.ny = (int)ny, a.nz = (int)nz, a.ldx = ldx, a.plane = ldx * ny;
+  a.x0 = p->x0, a.x1 = p->x1, a.y0 = p->y0, a.y1 = p->y1, a.z0 = p->z0, a.z1 = p->z1;
+  if (p->range_kind == B200ISO_RANGE_F32) a.x0 = (float)a.x0, a.x1 = (float)a.x1, a.y0 = (float)a.y0, a.y1 = (float)a.y1, a.z0 = (float)a.z0, a.z1 = (float)a.z1;
+  a.x_offset = p->x_offset, a.nx_global = p->nx_global > 0 ? p->nx_global : nx;
+  a.verts = verts_dev, a.vert_is_f64 = vert_is_f64, a.nverts = nverts, a.normals = normals_dev;
+  const unsigned nb = (unsigned)((nverts + 255) / 256);
+  if (p->field_is_f64) {
+    if (vert_is_f64) iso::vertex_normals_kernel<double, double><<<nb, 256, 0, h->stream>>>(a);
+    else iso::vertex_normals_kernel<double, float><<<nb, 256, 0, h->stream>>>(a);
+  } else {
+    if (vert_is_f64) iso::vertex_normals_kernel<float, double><<<nb, 256, 0, h->stream>>>(a);
+    else iso::vertex_normals_kernel<float, float><<<nb, 256, 0, h->stream>>>(a);
+  }
+  CU(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int b200iso_vertex_keys_async(b200iso_handle* h, int64_t* keys_dev, int64_t kcap) {
+  if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  if (!h->counted) return fail(B200ISO_ESTATE, "vertex keys need a counted field (b200iso_count / b200iso_count_async first)");
+  if (h->prm.algo != B200ISO_MC) return fail(B200ISO_EINVAL, "vertex keys are for Marching Cubes (Marching Tetrahedra vertices are already shared)");
+  if (kcap < 0 || (kcap > 0 && !keys_dev)) return fail(B200ISO_EINVAL, "bad keys buffer");
+  if (h->nblocks == 0) return 0;
+  DeviceGuard guard(h->device);
+  iso::GenArgs a{};
+  a.bits = h->bits.p, a.woff = h->woff.p, a.coords = h->coords.p, a.recs = h->recs.p, a.nrecs = h->nrecs.p;
+  a.verts = keys_dev, a.vcap = kcap, a.fcap = 0, a.nblocks = h->nblocks, a.totals_a = h->totals_dev, a.abort_flag = nullptr;
+  a.key_nx_global = h->prm.nx_global > 0 ? h->prm.nx_global : h->grid.nx;
+  iso::mc_generate_kernel<0, float, true><<<(unsigned)h->nblocks, iso::CB_THREADS, 0, h->stream>>>(a, h->grid);
+  CU(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+static int b200iso_weld_impl(b200iso_handle* h, const int64_t* keys_dev, const void* verts_dev, int64_t nverts, int vert_is_f64,
+                             const int64_t* faces_dev, int64_t nfaces, int64_t vertex_base, void* verts_out_dev, int64_t* faces_out_dev,
+                             int64_t* nwelded) {
+  if (!h) return fail(B200ISO_EINVAL, "handle is NULL");
+  if (nverts < 0 || nfaces < 0 || nverts >= (1ll << 31)) return fail(B200ISO_EINVAL, "bad sizes (at most 2^31 - 1 vertices)");
+  if (nwelded) *nwelded = 0;
+  if (nverts == 0) return 0;
+  if (!keys_dev || !verts_dev || !verts_out_dev || (nfaces > 0 && (!faces_dev || !faces_out_dev))) return fail(B200ISO_EINVAL, "NULL argument");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = h->stream;
+  unsigned long long slots = 1;
+  while (slots < 2ull * (unsigned long long)nverts) slots <<= 1;
+  if (int rc = h->weld_tab.reserve((size_t)slots * 2)) return rc;
+  if (int rc = h->weld_u32.reserve((size_t)nverts * 3 + 4)) return rc;
+  unsigned long long* tab_key = h->weld_tab.p;
+  long long* tab_min = reinterpret_cast<long long*>(h->weld_tab.p + slots);
+  unsigned int *slot_of = h->weld_u32.p, *keep = slot_of + nverts, *newidx = keep + nverts;
+  CU(cudaMemsetAsync(tab_key, 0, slots * sizeof(unsigned long long), st));
+  CU(cudaMemsetAsync(tab_min, 0xff, slots * sizeof(long long), st));  // (unsigned max: atomicMin on the unsigned view)
+  const unsigned nb = (unsigned)((nverts + 255) / 256);
+  iso::weld_insert_kernel<<<nb, 256, 0, st>>>((const long long*)keys_dev, nverts, tab_key, tab_min, slots - 1, slot_of);
+  iso::weld_flag_kernel<<<nb, 256, 0, st>>>(slot_of, tab_min, nverts, keep);
+  CU(cudaGetLastError());
+  size_t tmp_bytes = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, keep, newidx, (int)nverts, st));
+  if (int rc = h->weld_tmp.reserve(tmp_bytes + 16)) return rc;
+  CU(cub::DeviceScan::ExclusiveSum(h->weld_tmp.p, tmp_bytes, keep, newidx, (int)nverts, st));
+  if (vert_is_f64) iso::weld_compact_kernel<double><<<nb, 256, 0, st>>>((const double*)verts_dev, keep, newidx, nverts, (double*)verts_out_dev);
+  else iso::weld_compact_kernel<float><<<nb, 256, 0, st>>>((const float*)verts_dev, keep, newidx, nverts, (float*)verts_out_dev);
+  if (nfaces > 0)
+    iso::weld_faces_kernel<<<(unsigned)((nfaces * 3 + 255) / 256), 256, 0, st>>>((const long long*)faces_dev, nfaces * 3, vertex_base, slot_of, tab_min,
+                                                                                newidx, (long long*)faces_out_dev);
+  CU(cudaGetLastError());
+  h->launches += 5;
+  unsigned int last[2] = {0, 0};
+  CU(cudaMemcpyAsync(&last[0], newidx + nverts - 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(&last[1], keep + nverts - 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (nwelded) *nwelded = (int64_t)last[0] + last[1];
+  return 0;
+}
+
+int b200iso_weld(b200iso_handle* h, const int64_t* keys_dev, const void* verts_dev, int64_t nverts, int vert_is_f64, const int64_t* faces_dev,
+                 int64_t nfaces, int64_t vertex_base, void* verts_out_dev, int64_t* faces_out_dev, int64_t* nwelded) {
+  try {
+    return b200iso_weld_impl(h, keys_dev, verts_dev, nverts, vert_is_f64, faces_dev, nfaces, vertex_base, verts_out_dev, faces_out_dev, nwelded);
+  } catch (const std::exception& e) {
+    return fail(B200ISO_ENOMEM, "b200iso_weld: %s", e.what());
+  } catch (...) {
+    return fail(B200ISO_ENOMEM, "b200iso_weld: unknown C++ exception");
+  }
+}
+
+// Binary little-endian PLY: vertex x y z (float or double) [+ nx ny nz float], face = uchar 3 + 3 x int32 (0-based).
+int b200iso_write_ply(const char* path, const void* verts, int64_t nverts, int vert_is_f64, const float* normals, const int64_t* faces,
+                      int64_t nfaces) {
+  if (!path || nverts < 0 || nfaces < 0 || (nverts > 0 && !verts) || (nfaces > 0 && !faces)) return fail(B200ISO_EINVAL, "bad argument");
+  if (nverts >= (1ll << 31)) return fail(B200ISO_EINVAL, "PLY faces are written with 32-bit indices: at most 2^31 - 1 vertices");
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(B200ISO_EINVAL, "cannot open %s for writing", path);
+  const char* vt = vert_is_f64 ? "double" : "float";
+  fprintf(f, "ply\nformat binary_little_endian 1.0\ncomment written by libb200iso\nelement vertex %lld\nproperty %s x\nproperty %s y\nproperty %s z\n",
+          (long long)nverts, vt, vt, vt);
+  if (normals) fprintf(f, "property float nx\nproperty float ny\nproperty float nz\n");
+  fprintf(f, "element face %lld\nproperty list uchar int vertex_indices\nend_header\n", (long long)nfaces);
+  const size_t vsz = vert_is_f64 ? 8 : 4;
+  bool ok = true;
+  if (!normals) {
+    ok = fwrite(verts, 3 * vsz, (size_t)nverts, f) == (size_t)nverts;
+  } else {
+    std::vector<unsigned char> row(3 * vsz + 12);
+    for (int64_t i = 0; i < nverts && ok; ++i) {
+      memcpy(row.data(), (const unsigned char*)verts + (size_t)i * 3 * vsz, 3 * vsz);
+      memcpy(row.data() + 3 * vsz, normals + 3 * i, 12);
+      ok = fwrite(row.data(), row.size(), 1, f) == 1;
+    }
+  }
+  std::vector<unsigned char> buf;
+  buf.reserve((size_t)13 * 4096);
+  for (int64_t i = 0; i < nfaces && ok; ++i) {
+    const int32_t t[3] = {(int32_t)(faces[3 * i] - 1), (int32_t)(faces[3 * i + 1] - 1), (int32_t)(faces[3 * i + 2] - 1)};
+    buf.push_back(3);
+    buf.insert(buf.end(), (const unsigned char*)t, (const unsigned char*)t + 12);
+    if (buf.size() >= (size_t)13 * 4096 || i == nfaces - 1) {
+      ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+      buf.clear();
+    }
+  }
+  ok = (fclose(f) == 0) && ok;
+  return ok ? 0 : fail(B200ISO_EINVAL, "short write to %s", path);
+}
+
+// Binary STL: 80-byte header, uint32 count, per triangle: float normal[3] (of the triangle), 3 x float vertex[3], uint16 0.
+int b200iso_write_stl(const char* path, const void* verts, int64_t nverts, int vert_is_f64, const int64_t* faces, int64_t nfaces) {
+  if (!path || nverts < 0 || nfaces < 0 || (nverts > 0 && !verts) || (nfaces > 0 && !faces)) return fail(B200ISO_EINVAL, "bad argument");
+  if (nfaces >= (1ll << 32)) return fail(B200ISO_EINVAL, "binary STL holds at most 2^32 - 1 triangles");
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(B200ISO_EINVAL, "cannot open %s for writing", path);
+  char hdr[80];
+  memset(hdr, 0, sizeof(hdr));
+  snprintf(hdr, sizeof(hdr), "binary STL written by libb200iso");
+  const uint32_t n32 = (uint32_t)nfaces;
+  bool ok = fwrite(hdr, 1, 80, f) == 80 && fwrite(&n32, 4, 1, f) == 1;
+  auto vtx = [&](int64_t idx, float out[3]) {
+    for (int q = 0; q < 3; ++q) out[q] = vert_is_f64 ? (float)((const double*)verts)[3 * idx + q] : ((const float*)verts)[3 * idx + q];
+  };
+  std::vector<unsigned char> buf;
+  buf.reserve((size_t)50 * 4096);
+  for (int64_t i = 0; i < nfaces && ok; ++i) {
+    float rec[12];
+    for (int c = 0; c < 3; ++c) {
+      const int64_t idx = faces[3 * i + c] - 1;
+      if (idx < 0 || idx >= nverts) {
+        fclose(f);
+        return fail(B200ISO_EINVAL, "face %lld references vertex %lld of %lld", (long long)i, (long long)(idx + 1), (long long)nverts);
+      }
+      vtx(idx, rec + 3 + 3 * c);
+    }
+    const float u[3] = {rec[6] - rec[3], rec[7] - rec[4], rec[8] - rec[5]}, w[3] = {rec[9] - rec[3], rec[10] - rec[4], rec[11] - rec[5]};
+    float n[3] = {u[1] * w[2] - u[2] * w[1], u[2] * w[0] - u[0] * w[2], u[0] * w[1] - u[1] * w[0]};
+    const float len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    for (int q = 0; q < 3; ++q) rec[q] = len > 0 ? n[q] / len : 0.f;
+    const uint16_t attr = 0;
+    buf.insert(buf.end(), (const unsigned char*)rec, (const unsigned char*)rec + 48);
+    buf.insert(buf.end(), (const unsigned char*)&attr, (const unsigned char*)&attr + 2);
+    if (buf.size() >= (size_t)50 * 4096 || i == nfaces - 1) {
+      ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+      buf.clear();
+    }
+  }
+  ok = (fclose(f) == 0) && ok;
+  return ok ? 0 : fail(B200ISO_EINVAL, "short write to %s", path);
 }
 
 int b200iso_enable_timing(b200iso_handle* h, int on) {

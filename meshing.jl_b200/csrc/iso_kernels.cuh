@@ -621,6 +621,7 @@ struct GenArgs {
   int sdf_vec;                           // Float32 field, base 16-byte aligned, ldx % 4 == 0: aligned pair loads
   const uint32_t* recs;          // MC: active-voxel records of every generate block (REC_CAP each), written by the count
   const uint32_t* nrecs;         // MC: active voxels per generate block
+  long long key_nx_global;       // KEYS instantiation: samples along x of the whole volume
   long long nblocks;
   const long long* totals_a;     // device totals {nverts, nfaces} of the count
   const long long* abort_flag;   // != 0: a peer exchange ahead of this kernel failed -- emit nothing
@@ -776,7 +777,9 @@ __device__ __forceinline__ void store3(S* base, long long gi, S v0, S v1, S v2, 
 // plus its packed face list (ISO_MC_FACES[case]) in recf[].  The per-case tables are read once per voxel (B1b) --
 // not once per vertex and once per face: each of those was a 32-address gather into a 2 KB table, i.e. up to 16 L1
 // line look-ups per warp instruction, and the kernel is bound by L1 line look-ups.
-template <int MODE, typename V>
+// KEYS = true (mesh consumers, mesh_consumers.cuh): instead of the vertices, write every vertex's grid-edge key
+// (3 * linear index of the edge's lower end node in the WHOLE volume + axis) as Int64 into a.verts; no faces.
+template <int MODE, typename V, bool KEYS = false>
 __global__ void __launch_bounds__(CB_THREADS, ISO_GEN_MINB)
 mc_generate_kernel(GenArgs a, Grid g) {
   __shared__ uint32_t s_w[CB_THREADS / 32];
@@ -877,7 +880,7 @@ mc_generate_kernel(GenArgs a, Grid g) {
       *reinterpret_cast<uint2*>(&rec[r1].z) = make_uint2((uint32_t)tv, (uint32_t)(tv >> 32) & 0xffffu);
       nvf1 = (uint32_t)((tv >> 48) & 15) | ((uint32_t)((tv >> 52) & 7) << 16);
     }
-    {
+    if constexpr (!KEYS) {
       const bool vec = sizeof(T) == 4 && a.sdf_vec;
       const int ph = x & 3;
       const T* fld = reinterpret_cast<const T*>(a.sdf) + x;
@@ -957,6 +960,14 @@ mc_generate_kernel(GenArgs a, Grid g) {
       const uint32_t ca = e & 7u, cb = e < 8u ? ((e & 4u) | ((e + 1u) & 3u)) : e - 4u;
       // MC corner offsets (dx | dy<<1 | dz<<2) for corners 0..7: 0,1,3,2,4,5,7,6
       const uint32_t oa = (0x67542310u >> (4 * ca)) & 7u, ob = (0x67542310u >> (4 * cb)) & 7u;
+      if constexpr (KEYS) {
+        // the edge's end nodes differ in exactly one axis: oa & ob is the lower one, oa ^ ob the axis bit
+        const uint32_t lo_n = oa & ob, ax = oa ^ ob;
+        const long long nxg = a.key_nx_global, node = (long long)(x + g.xoff + (lo_n & 1u)) +
+                              nxg * ((long long)((r.x & 0xffffu) + ((lo_n >> 1) & 1u)) + (long long)g.ny * (long long)((r.x >> 16) + (lo_n >> 2)));
+        if ((long long)bv + k < a.vcap) reinterpret_cast<long long*>(a.verts)[(long long)bv + k] = 3 * node + (ax == 1u ? 0 : ax == 2u ? 1 : 2);
+        continue;
+      }
       T va, vb;
       if constexpr (sizeof(T) == 4) {  // (chunk swizzle of the corner store, see B1b)
         const T* cp = &corner[s & ~1u][0];
@@ -981,7 +992,7 @@ mc_generate_kernel(GenArgs a, Grid g) {
       if (vfits || (long long)bv + k < a.vcap) store3<V>(verts, (long long)bv + k, (V)p[0], (V)p[1], (V)p[2], vwide);
     }
     // ---- B3: thread per face ----
-    for (uint32_t k = tid; k < nfr; k += CB_THREADS) {
+    for (uint32_t k = tid; !KEYS && k < nfr; k += CB_THREADS) {
       const uint32_t s = owner_f[k];
       const uint32_t ry = rec[s].y;
       const uint32_t fi = k - (ry >> 16);
