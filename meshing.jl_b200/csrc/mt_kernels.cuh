@@ -126,6 +126,9 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
   __shared__ uint32_t rank0_s[256];            // ISO_MT_RANK0
   __shared__ uint8_t nown0_s[256], nf_s[256];
 #endif
+  __shared__ uint32_t emask_s[8];               // edges (bit e - 1) by the axes on which their owner is the previous voxel
+  __shared__ int32_t nb_base[MTG_NB * 8];       // per (voxel, lower neighbour): id of the neighbour's first vertex, relative to bv ...
+  __shared__ uint16_t nb_info[MTG_NB * 8];      // ... and its case | low-boundary flags << 8
   __shared__ uint8_t slot_s[20];               // ISO_MT_OWN_SLOT
   __shared__ uint16_t einfo_s[20];
   __shared__ uint8_t eshift_s[160];
@@ -164,6 +167,12 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
 #endif
   for (int i = tid; i < 20; i += CB_THREADS) einfo_s[i] = ISO_MT_EDGE_INFO[i], slot_s[i] = ISO_MT_OWN_SLOT[i];
   for (int i = tid; i < 160; i += CB_THREADS) eshift_s[i] = ISO_MT_EDGE_SHIFT[i];
+  if (tid < 8) {
+    uint32_t m = 0;
+    for (int e = 1; e <= 19; ++e)
+      if (((ISO_MT_EDGE_INFO[e] >> 6) & 7) == tid) m |= 1u << (e - 1);
+    emask_s[tid] = m;
+  }
   // The count left the block's active-voxel records (scan order) unless there are more than REC_CAP of them: then
   // (dense fields) this block derives them from the bit-field itself (A + B1a).
   const uint32_t nrec = __ldg(a.nrecs + b);
@@ -238,7 +247,47 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
     }
     __syncthreads();
     const uint32_t rv0 = wv, rf0 = 0;
-    // ---- B1c: thread per (voxel, crossed edge): resolve the vertex id through the owner voxel ----
+    // ---- B1c: vertex id of every crossed edge, through the voxel that OWNS the edge (mt_kernels.cuh header).
+    // The owner of a foreign edge is one of the 7 lower neighbours (shift sh = 1..7: -1 along x / y / z for bits 0 / 1 / 2);
+    // its case and the id of its first vertex come from the bit-field, the block prefixes and celloff -- the expensive
+    // part -- and several crossed edges usually share one owner.  So (1) a thread per (voxel, neighbour) resolves each
+    // NEEDED neighbour once, then (2) a thread per (voxel, crossed edge) only looks the edge's rank up in the owner's list.
+    for (uint32_t it = tid; it < cnt * 8; it += CB_THREADS) {
+      const uint32_t s = it >> 3;
+      const int sh = (int)(it & 7u);
+      const uint32_t vc = rec_vc[s], yz = rec_yc[s].x;
+      const uint32_t cm = MT_CROSS_S(vc >> 24);
+      const int vy = (int)(yz & 0xffffu), vz = (int)(yz >> 16);
+      const int flags = fx | (vy == 0 ? 2 : 0) | (vz == 0 ? 4 : 0);
+      // crossed edges whose owner is neighbour sh: low-axes L with L & ~flags == sh, i.e. L = sh | m for m within flags
+      uint32_t mine = 0;
+      if (sh != 0 && (sh & flags) == 0) {
+        mine = emask_s[sh];
+        if (flags & 1) mine |= emask_s[sh | 1];
+        if (flags & 2) mine |= emask_s[sh | 2];
+        if (flags & 4) mine |= emask_s[sh | 4];
+        if ((flags & 3) == 3) mine |= emask_s[sh | 3];
+        if ((flags & 5) == 5) mine |= emask_s[sh | 5];
+        if ((flags & 6) == 6) mine |= emask_s[sh | 6];
+        // (flags == 7 leaves sh == 0 only)
+      }
+      if ((mine & cm) == 0) continue;
+      const int ox = x - (sh & 1), oy = vy - ((sh >> 1) & 1), oz = vz - (sh >> 2);
+      const int oflags = ((ox + g.xoff) == 0 ? 1 : 0) | (oy == 0 ? 2 : 0) | (oz == 0 ? 4 : 0);
+      Quad q;
+      load_cell(a.bits, g, ox, oy, oz >> 5, q);
+      const int k = oz & 31;
+      const uint32_t oc = case_of<1>(q, 0, k);
+      // vertices created before the owner voxel: block prefix + cell prefix + in-cell prefix
+      const uint32_t below = q.vm[0] & ((1u << k) - 1u);
+      const uint32_t incell = mt_owned_masked(q, 0, below, oflags & 3, (oz >> 5) == 0);
+      const long long ob = (long long)ox * g.blocks_per_row + (oy * g.Wq + (oz >> 7)) / CB_THREADS;  // the owner's block
+      const unsigned long long obv = ob > 0 ? (a.status[2 * (ob - 1)] & VAL_MASK) : 0ull;
+      const uint32_t co = __ldg(celloff + (long long)ox * g.row_words + (long long)oy * g.W + (oz >> 5));
+      nb_base[it] = (int32_t)((long long)(obv + co + incell) - (long long)bv);
+      nb_info[it] = (uint16_t)(oc | ((uint32_t)oflags << 8));
+    }
+    __syncthreads();
     for (uint32_t it = tid; it < cnt * MTG_EDGES; it += CB_THREADS) {
       const uint32_t s = it / MTG_EDGES, j = it - s * MTG_EDGES;
       const uint32_t vc = rec_vc[s], yz = rec_yc[s].x;
@@ -246,45 +295,26 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
       const uint32_t cm = MT_CROSS_S(c);
       if (j >= (uint32_t)__popc(cm)) continue;
       // j-th crossed edge (ascending id), 1..19: from the per-case list; a 13th is the highest crossed edge
-      const int e = j < 12 ? (int)((MT_CLIST_S(c) >> (5 * j)) & 31u) : 32 - __clz(cm);
+      int e = j < 12 ? (int)((MT_CLIST_S(c) >> (5 * j)) & 31u) : 32 - __clz(cm);
       const int vy = (int)(yz & 0xffffu), vz = (int)(yz >> 16);
-      const int flags = fx | (vy == 0 ? 2 : 0) | (vz == 0 ? 4 : 0);
-      const int low = (einfo_s[e] >> 6) & 7;
-      const int sh = low & ~flags;  // axes on which the owner is the previous voxel
-      int32_t id;
-      if (sh == 0) {  // this voxel owns the edge
-        int r = 0;
-        if (flags == 0) {  // interior voxel: rank of an interior-owned edge from the per-case table
-          r = (int)((MT_RANK0_S(c) >> (3 * slot_s[e])) & 7u);
-        } else {
-          const unsigned long long ow = owned_word(c, flags);
-          while (((ow >> (5 * r)) & 31u) != (unsigned)e) ++r;
-        }
-        id = (int32_t)(vc & 0xffffffu) + r;
-      } else {
-        const int ox = x - (sh & 1), oy = vy - ((sh >> 1) & 1), oz = vz - (sh >> 2);
-        const int eo = eshift_s[e * 8 + sh];  // the same edge in the owner's frame
-        const int oflags = ((ox + g.xoff) == 0 ? 1 : 0) | (oy == 0 ? 2 : 0) | (oz == 0 ? 4 : 0);
-        Quad q;
-        load_cell(a.bits, g, ox, oy, oz >> 5, q);
-        const int k = oz & 31;
-        const uint32_t oc = case_of<1>(q, 0, k);
-        int r = 0;
-        if (oflags == 0) {
-          r = (int)((MT_RANK0_S(oc) >> (3 * slot_s[eo])) & 7u);
-        } else {
-          const unsigned long long ow = owned_word(oc, oflags);
-          while (((ow >> (5 * r)) & 31u) != (unsigned)eo) ++r;
-        }
-        // vertices created before the owner voxel: block prefix + cell prefix + in-cell prefix
-        const uint32_t below = q.vm[0] & ((1u << k) - 1u);
-        const uint32_t incell = mt_owned_masked(q, 0, below, oflags & 3, (oz >> 5) == 0);
-        const long long ob = (long long)ox * g.blocks_per_row + (oy * g.Wq + (oz >> 7)) / CB_THREADS;  // the owner's block
-        const unsigned long long obv = ob > 0 ? (a.status[2 * (ob - 1)] & VAL_MASK) : 0ull;
-        const uint32_t co = __ldg(celloff + (long long)ox * g.row_words + (long long)oy * g.W + (oz >> 5));
-        id = (int32_t)((long long)(obv + co + incell + r) - (long long)bv);
+      int flags = fx | (vy == 0 ? 2 : 0) | (vz == 0 ? 4 : 0);
+      const int sh = ((einfo_s[e] >> 6) & 7) & ~flags;  // axes on which the owner is the previous voxel
+      uint32_t oc = c;
+      int32_t base = (int32_t)(vc & 0xffffffu);
+      if (sh != 0) {  // foreign edge: the owner's case / flags / first vertex, and the edge's name in the owner's frame
+        const uint32_t info = nb_info[s * 8 + sh];
+        base = nb_base[s * 8 + sh];
+        oc = info & 0xffu, flags = (int)(info >> 8);
+        e = eshift_s[e * 8 + sh];
       }
-      evid[s * MTG_EDGES + j] = id;
+      int r = 0;
+      if (flags == 0) {  // interior owner: rank of an interior-owned edge from the per-case table
+        r = (int)((MT_RANK0_S(oc) >> (3 * slot_s[e])) & 7u);
+      } else {
+        const unsigned long long ow = owned_word(oc, flags);
+        while (((ow >> (5 * r)) & 31u) != (unsigned)e) ++r;
+      }
+      evid[s * MTG_EDGES + j] = base + r;
     }
     __syncthreads();
     const uint32_t nvr = wtot & 0xffffu, nfr = wtot >> 16;
