@@ -236,7 +236,8 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
     if (int rc = h->status.reserve((size_t)h->nblocks * 2)) return rc;
     if (int rc = h->celloff.reserve(nbits)) return rc;
   }
-  if (int rc = h->recs.reserve((size_t)h->nblocks * iso::REC_CAP + 2)) return rc;
+  g.rec_cap = iso::rec_cap_for(h->nblocks);
+  if (int rc = h->recs.reserve((size_t)h->nblocks * g.rec_cap + 2)) return rc;
   if (int rc = h->nrecs.reserve((size_t)h->nblocks)) return rc;
   if (int rc = h->coords.reserve((size_t)(nx + ny + nz))) return rc;
   unsigned int* ticket = reinterpret_cast<unsigned int*>(h->chain.p);

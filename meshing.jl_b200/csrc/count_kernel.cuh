@@ -39,7 +39,7 @@ mt_count_kernel(const uint32_t* __restrict__ bits, Grid g, uint32_t* __restrict_
   uint32_t pos = block_excl_scan_u32(na, s_w, blk_na);
   if (na) {
     const int fxy = ((tm.x + g.xoff) == 0 ? 1 : 0) | (tm.y == 0 ? 2 : 0);  // low-boundary flags use GLOBAL x
-    uint32_t* rec = recs + (unsigned long long)b * REC_CAP;
+    uint32_t* rec = recs + (unsigned long long)b * (unsigned)g.rec_cap;
     const uint32_t qtag = (uint32_t)threadIdx.x << 15;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -52,7 +52,7 @@ mt_count_kernel(const uint32_t* __restrict__ bits, Grid g, uint32_t* __restrict_
           mm &= mm - 1;
           const uint32_t c = case_of<1>(q, i, k);
           nf += nf_s[c];
-          if (pos < (uint32_t)REC_CAP) rec[pos] = c | ((uint32_t)(i * 32 + k) << 8) | qtag;
+          if (pos < (uint32_t)g.rec_cap) rec[pos] = c | ((uint32_t)(i * 32 + k) << 8) | qtag;
           ++pos;
         }
       }

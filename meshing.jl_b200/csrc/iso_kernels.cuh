@@ -45,6 +45,7 @@ struct Grid {
   long long plane;       // ldx * ny
   int xoff;              // global index of the slab's first sample plane (x-slab sharding; 0 otherwise)
   int ghost;             // MT sharding: voxel row 0 belongs to the previous slab (counted, not emitted)
+  int rec_cap;           // active-voxel records kept per generate block (REC_CAP_MIN .. REC_CAP_MAX, set by the host)
   // exact division by Wq and blocks_per_row without the ~45-instruction integer divide (every thread of every
   // count/generate block maps itself to (x, y, zq) with them): q = (umulhi(n, M) + n) >> s  (Granlund-Montgomery)
   unsigned wq_mul, wq_sh, bpr_mul, bpr_sh;
@@ -343,7 +344,16 @@ __device__ __forceinline__ uint32_t mc_nverts_masked(const Quad& q, int i, uint3
 // in nrecs[chunk].  generate then starts from the records instead of re-deriving them from the bit-field (its
 // thread mapping, quad-cell loads, active masks, block scan and case extraction were a third of its instructions);
 // a block with more than REC_CAP active voxels (dense fields) takes generate's own front end instead.
-constexpr int REC_CAP = 512;  // records per generate block (2 KB): 3 % of its 16384 voxels; the 1024^3 gyroid averages 155
+// Records per generate block: 512 (2 KB: 3 % of the block's 16384 voxels; the 1024^3 gyroid averages 155 per block, and
+// the record array is then as large as the bit-field) on big grids, up to 4096 on small ones, where a block of a
+// surface-like field holds more active voxels (16384 * 3.8 % = 620 at 256^3) and the array is small anyway.
+constexpr int REC_CAP_MIN = 512, REC_CAP_MAX = 4096;
+inline int rec_cap_for(long long nblocks) {
+  const long long budget = (64ll << 20) / 4;  // records that fit 64 MB
+  long long cap = nblocks > 0 ? budget / nblocks : REC_CAP_MAX;
+  cap = cap / 256 * 256;
+  return (int)(cap < REC_CAP_MIN ? REC_CAP_MIN : cap > REC_CAP_MAX ? REC_CAP_MAX : cap);
+}
 template <bool CG>
 __device__ __forceinline__ void mc_count_chunk(const uint32_t* __restrict__ bits, const Grid& g, long long chunk, const uint8_t* nf_s,
                                                uint32_t* __restrict__ recs, uint32_t* __restrict__ nrecs, uint32_t& nv_out, uint32_t& nf_out) {
@@ -351,7 +361,7 @@ __device__ __forceinline__ void mc_count_chunk(const uint32_t* __restrict__ bits
   uint32_t nv = 0, nf = 0, base = 0;  // base: active voxels of the block before this group of 32 quad-cells (uniform)
   const int x = (int)(chunk / g.blocks_per_row);
   const int q_lo = (int)(chunk - (long long)x * g.blocks_per_row) * CB_THREADS;
-  uint32_t* rec = recs + chunk * REC_CAP;
+  uint32_t* rec = recs + chunk * g.rec_cap;
   for (int q0 = q_lo; q0 < q_lo + CB_THREADS && q0 < g.quads_per_row; q0 += 32) {
     const int qr = q0 + lane;
     const int y = (int)fast_div((unsigned)qr, g.wq_mul, g.wq_sh), zq = qr - y * g.Wq;
@@ -384,7 +394,7 @@ __device__ __forceinline__ void mc_count_chunk(const uint32_t* __restrict__ bits
             m &= m - 1;
             const uint32_t c = case_of<0>(q, i, k);
             nf += nf_s[c];
-            if (pos < (uint32_t)REC_CAP) rec[pos] = c | ((uint32_t)(i * 32 + k) << 8) | qtag;
+            if (pos < (uint32_t)g.rec_cap) rec[pos] = c | ((uint32_t)(i * 32 + k) << 8) | qtag;
             ++pos;
           }
         }
@@ -805,7 +815,7 @@ mc_generate_kernel(GenArgs a, Grid g) {
   // The count left the block's active-voxel records (scan order) unless there are more than REC_CAP of them: then
   // (dense fields) this block derives them from the bit-field itself (A + B1a below).
   const uint32_t nrec = __ldg(a.nrecs + b);
-  const bool from_recs = nrec <= (uint32_t)REC_CAP;  // (uniform over the block)
+  const bool from_recs = nrec <= (uint32_t)g.rec_cap;  // (uniform over the block)
   TMap tm;
   tm.x = (int)fast_div(b, g.bpr_mul, g.bpr_sh);
   const uint32_t q_lo = (b - (unsigned)tm.x * (unsigned)g.blocks_per_row) * CB_THREADS;  // first quad-cell of the block in its x-row
@@ -852,7 +862,7 @@ mc_generate_kernel(GenArgs a, Grid g) {
     uint2 rc0 = make_uint2(0, 0), rc1 = make_uint2(0, 0);  // (y | z << 16, case) of the two records
     if (from_recs) {
       // the count's records: case | voxel-in-quad-cell << 8 | quad-cell-in-block << 15 (one aligned 8-byte load per thread)
-      const uint2 w = r0 < cnt ? __ldg(reinterpret_cast<const uint2*>(a.recs + (unsigned long long)b * REC_CAP + lo + r0)) : make_uint2(0, 0);
+      const uint2 w = r0 < cnt ? __ldg(reinterpret_cast<const uint2*>(a.recs + (unsigned long long)b * (unsigned)g.rec_cap + lo + r0)) : make_uint2(0, 0);
       auto decode = [&](uint32_t wd) {
         const uint32_t qr = q_lo + (wd >> 15), y = fast_div(qr, g.wq_mul, g.wq_sh), zq = qr - y * (uint32_t)g.Wq;
         return make_uint2(y | ((zq * 128u + ((wd >> 8) & 127u)) << 16), wd & 0xffu);

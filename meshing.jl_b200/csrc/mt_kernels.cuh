@@ -176,7 +176,7 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
   // The count left the block's active-voxel records (scan order) unless there are more than REC_CAP of them: then
   // (dense fields) this block derives them from the bit-field itself (A + B1a).
   const uint32_t nrec = __ldg(a.nrecs + b);
-  const bool from_recs = nrec <= (uint32_t)REC_CAP;  // (uniform over the block)
+  const bool from_recs = nrec <= (uint32_t)g.rec_cap;  // (uniform over the block)
   const uint32_t q_lo = (b - (unsigned)x * (unsigned)g.blocks_per_row) * CB_THREADS;  // first quad-cell of the block in its x-row
   uint32_t tna = 0, my_a0 = 0, blk_na = nrec;
   if (!from_recs) {
@@ -219,7 +219,7 @@ mt_generate_kernel(GenArgs a, Grid g, const uint32_t* __restrict__ celloff) {
     // ---- B1a: records (position, case) of the window's voxels, in scan order ----
     if (from_recs) {
       if ((uint32_t)tid < cnt) {  // the count's record: case | voxel-in-quad-cell << 8 | quad-cell-in-block << 15
-        const uint32_t wd = __ldg(a.recs + (unsigned long long)b * REC_CAP + lo + tid);
+        const uint32_t wd = __ldg(a.recs + (unsigned long long)b * (unsigned)g.rec_cap + lo + tid);
         const uint32_t qr = q_lo + (wd >> 15), y = qr / (uint32_t)g.Wq, zq = qr - y * (uint32_t)g.Wq;
         rec_yc[tid] = make_uint2(y | ((zq * 128u + ((wd >> 8) & 127u)) << 16), wd & 0xffu);
       }
