@@ -474,10 +474,16 @@ def e2e_run(ctx, r, steps):
            "h2d_bytes_per_step": 4 * nxl * ny * nz, "d2h_bytes_per_step": 3 * vsz * nv + 24 * nf + 16,
            "host_memory": head["host_memory"], "api": head["api"], ("pinned" if world == 1 else "pageable"): other}
     dt = head["ms_per_step"] * 1e-3
-    res["pcie_ceiling"] = pcie_ceiling(ctx)
+    res["pcie_ceiling"] = pc = pcie_ceiling(ctx)
     h2d_rate = res["h2d_bytes_per_step"] / dt / 1e9
     res["h2d_gbs_this_gpu"] = h2d_rate
-    res["frac_of_pinned_h2d_ceiling"] = h2d_rate / max(res["pcie_ceiling"]["h2d_gbs_this_gpu"], 1e-9)
+    res["frac_of_pinned_h2d_ceiling"] = h2d_rate / max(pc["h2d_gbs_this_gpu"], 1e-9)
+    # what the box allows for this step's bytes at the rates measured above with every GPU copying at once:
+    # both directions fully overlapped (duplex) / one after the other (sequential)
+    t_up = res["h2d_bytes_per_step"] / max(pc["h2d_gbs_this_gpu"], 1e-9) / 1e6
+    t_dn = res["d2h_bytes_per_step"] / max(pc["d2h_gbs_this_gpu"], 1e-9) / 1e6
+    res["pcie_bound_ms"] = {"duplex": max(t_up, t_dn), "sequential": t_up + t_dn,
+                            "note": "rank 0's bytes at rank 0's concurrent pinned H2D / D2H rates"}
     return res, hfield
 
 
