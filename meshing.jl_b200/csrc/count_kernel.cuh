@@ -90,17 +90,6 @@ mt_count_kernel(const uint32_t* __restrict__ bits, Grid g, uint32_t* __restrict_
 // 32 at a time) and stores the block's raw (vertex, face) pair -- no chain, no ticket, no barrier.
 constexpr int WC_THREADS = 256;  // 8 warps = 8 generate blocks per counting block
 
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
-    if (lane >= o) v += t;
-  }
-  return v;
-}
-
-// (launch bound 4 blocks/SM = 64 registers: with the record emission 40 registers spill 200+ bytes)
 // ride: the counting warps inside the TMA classify kernel (signpack_tma.cuh) have already counted every y-block
 // below ride[0] (cur_bi) and, of the y-blocks from there on, the generate blocks x < next_x[bi]; this kernel takes the
 // rest with a grid-stride loop (everything, starting at item 0, when ride == nullptr).  Items are numbered
