@@ -672,6 +672,8 @@ static int b200iso_generate_impl(b200iso_handle* h, void* verts, int64_t* faces,
         h->slab_ev.push_back(e);
       }
       CU(cudaEventRecord(h->slab_ev[0], h->stream));
+      hostpipe::advise_huge(verts, (size_t)h->nverts * 3 * vsz);
+      hostpipe::advise_huge(faces, (size_t)h->nfaces * 3 * sizeof(int64_t));
       hostpipe::Downloader down;
       CU(down.start(&h->pool, 1, false, h->slab_ev[0]));
       hostpipe::Downloader::Job j;
@@ -719,7 +721,12 @@ static int host_slab_pass(b200iso_handle* h, hostpipe::Uploader* up, void* verts
   const size_t vsz = h->hs_vf64 ? 8 : 4;
   const cudaEvent_t ev_fork = h->slab_ev[S];
   hostpipe::Downloader down;
-  CU(down.start(&h->pool, S, hostpipe::is_pinned(verts) && hostpipe::is_pinned(faces), ev_fork));
+  const bool out_pinned = hostpipe::is_pinned(verts) && hostpipe::is_pinned(faces);
+  if (!out_pinned) {  // fresh pageable result arrays: first touched by the download workers
+    hostpipe::advise_huge(verts, (size_t)std::max<int64_t>(0, vcap) * 3 * vsz);
+    hostpipe::advise_huge(faces, (size_t)std::max<int64_t>(0, fcap) * 3 * sizeof(int64_t));
+  }
+  CU(down.start(&h->pool, S, out_pinned, ev_fork));
   int64_t cv = 0, cf = 0;
   int njobs = 0;
   bool overflow = false;

@@ -19,10 +19,85 @@
 #include <cstring>
 #include <thread>
 #include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 
 namespace hostpipe {
 
-constexpr size_t CHUNK = (size_t)8 << 20;  // bytes per pinned staging chunk
+// Bytes per pinned staging chunk.  Measured at 1024^3 on the B200 host, whole pageable call, 24 workers
+// (profiles/r2_host_chunks.txt): 256 KB 238 ms, 512 KB 171 ms, 1 MB 124 ms (the per-copy driver cost, ~7 us under the
+// workers' contention, dominates), 2 MB 112-120 ms, 3 MB 119 ms, 4 MB 130 ms, 8 MB 120-136 ms.
+constexpr size_t CHUNK = (size_t)2 << 20;
+
+// experiment knobs, read per call: B200ISO_HOST_CHUNK_KB (<= 2048) and B200ISO_HOST_STREAM (bit 0: the upload's staging
+// copies use streaming stores, bit 1: the download's).  Default 2: the upload's chunks are read back by the DMA engine
+// while still in the last-level cache, so plain memcpy wins there (2 MB chunks: 112-120 ms against 120 streamed); the
+// download writes the caller's array once and never reads it, so it streams (pre-touched target: 76 against 47 GB/s).
+inline size_t chunk_bytes() {
+  if (const char* e = getenv("B200ISO_HOST_CHUNK_KB")) return std::max<size_t>(64 << 10, std::min<size_t>(CHUNK, (size_t)atoll(e) << 10));
+  return CHUNK;
+}
+inline int stream_copies() {
+  const char* e = getenv("B200ISO_HOST_STREAM");
+  return e ? atoi(e) : 2;
+}
+
+// Staging copy with streaming (non-temporal) stores: for a destination that is written once and not read by this core
+// again, filling it through the cache only costs a read-for-ownership of every line.  Measured on the B200 host (16 vCPU
+// Xeon, tools/copy_probe.cu, profiles/r2_copy_probe.txt; copies alone, no DMA), 12-16 threads: whole 4 KB rows 43-57 GB/s
+// with memcpy, 76-80 GB/s streamed; 1040-byte row pieces (4 x-slabs) 41-45 against 48-55 GB/s.
+// Callers end a batch of copies with copy_fence() before anything else may read the destination.
+inline void copy_stream(unsigned char* dst, const unsigned char* src, size_t n) {
+#if defined(__SSE2__)
+  if (n >= 256) {
+    const size_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+    if (head) memcpy(dst, src, head), dst += head, src += head, n -= head;
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+      const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+      const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 16));
+      const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 32));
+      const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 48));
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), a);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 16), b);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 32), c);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 48), d);
+    }
+    for (; i + 16 <= n; i += 16) _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i)));
+    dst += i, src += i, n -= i;
+  }
+#endif
+  if (n) memcpy(dst, src, n);
+}
+inline void copy_staged(unsigned char* dst, const unsigned char* src, size_t n, bool stream) {
+  if (stream) copy_stream(dst, src, n);
+  else memcpy(dst, src, n);
+}
+inline void copy_fence() {
+#if defined(__SSE2__)
+  _mm_sfence();
+#endif
+}
+
+// A freshly allocated result array is first touched by the download workers: 250 000 page faults per GB with 4 KB pages
+// (measured: 22 GB/s into fresh pages against 39 GB/s with transparent huge pages, 48-76 GB/s into touched ones).  Where
+// the kernel leaves huge pages to madvise (the B200 host: "always [madvise] never") ask for them on the 2 MB-aligned
+// interior of the caller's pageable output.  A hint only: contents and semantics are untouched; B200ISO_NO_HUGEPAGE=1 skips it.
+inline void advise_huge(void* p, size_t bytes) {
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+  static const bool off = getenv("B200ISO_NO_HUGEPAGE") != nullptr;
+  constexpr uintptr_t H = (uintptr_t)2 << 20;
+  if (off || !p || bytes < 4 * H) return;
+  const uintptr_t a = (reinterpret_cast<uintptr_t>(p) + H - 1) / H * H, b = (reinterpret_cast<uintptr_t>(p) + bytes) / H * H;
+  if (b > a) madvise(reinterpret_cast<void*>(a), b - a, MADV_HUGEPAGE);
+#else
+  (void)p, (void)bytes;
+#endif
+}
 
 inline bool is_pinned(const void* p) {
   if (!p) return true;
@@ -133,6 +208,8 @@ struct Uploader {
         Pool::Lane& L = pool->in[t];
         cudaError_t e = cudaSetDevice(pool->device);
         const size_t r0 = rows * t / T, r1 = rows * (t + 1) / T;
+        const size_t chunk = chunk_bytes();
+        const bool stream = (stream_copies() & 1) != 0;
         int tog = 0;
         for (int k = 0; k < S; ++k) {
           const Slab& sb = slabs[k];
@@ -143,15 +220,20 @@ struct Uploader {
                                            : cudaMemcpy2DAsync(sb.dst + r0 * dp, dp, src + r0 * spitch + xo, spitch, w, r1 - r0,
                                                                cudaMemcpyHostToDevice, L.stream);
             } else {
-              const size_t per = std::max<size_t>(1, CHUNK / dp);
+              const size_t per = std::max<size_t>(1, chunk / dp);
               for (size_t r = r0; r < r1 && e == cudaSuccess; r += per) {
                 const size_t n = std::min(per, r1 - r);
                 e = cudaEventSynchronize(L.buf_ev[tog]);  // the chunk's previous DMA has drained
                 if (e != cudaSuccess) break;
                 unsigned char* b = L.buf[tog];
-                if (w == spitch && w == dp) memcpy(b, src + r * spitch, n * w);
+                if (w == spitch && w == dp) copy_staged(b, src + r * spitch, n * w, stream);
                 else
-                  for (size_t i = 0; i < n; ++i) memcpy(b + i * dp, src + (r + i) * spitch + xo, w);  // (pad bytes: never read as samples)
+                  // every staged row is written over its whole pitch, pad included (the pad is never read as samples): a row
+                  // that ends inside a cache line would leave the line to be flushed half-written and finished by the next
+                  // row (measured: 8 slabs of 516-byte rows 345 ms per call against 140 with memcpy).  The few bytes past
+                  // the piece come from the same source row or the next one; the array's last row is copied exactly.
+                  for (size_t i = 0; i < n; ++i) copy_staged(b + i * dp, src + (r + i) * spitch + xo, r + i + 1 < rows ? dp : w, stream);
+                copy_fence();  // the streamed lines are in memory before the DMA is told to read them
                 e = cudaMemcpyAsync(sb.dst + r * dp, b, n * dp, cudaMemcpyHostToDevice, L.stream);
                 if (e == cudaSuccess) e = cudaEventRecord(L.buf_ev[tog], L.stream);
                 tog ^= 1;
@@ -219,6 +301,8 @@ struct Downloader {
       threads.emplace_back([=]() {
         Pool::Lane& L = pool->out[t];
         cudaError_t e = cudaSetDevice(pool->device);
+        const size_t chunk = chunk_bytes();
+        const bool stream = (stream_copies() & 2) != 0;
         for (int k = 0;; ++k) {
           while (njobs.load(std::memory_order_acquire) <= k && !closed.load(std::memory_order_acquire)) nap();
           if (njobs.load(std::memory_order_acquire) <= k) break;
@@ -229,21 +313,22 @@ struct Downloader {
             const size_t a = j.bytes[part] * t / T / 16 * 16, b = t == T - 1 ? j.bytes[part] : j.bytes[part] * (t + 1) / T / 16 * 16;
             size_t pend_off = 0, pend_n = 0;
             int pend_buf = -1, tog = 0;
-            for (size_t off = a; off < b && e == cudaSuccess; off += CHUNK) {
-              const size_t n = std::min(CHUNK, b - off);
+            for (size_t off = a; off < b && e == cudaSuccess; off += chunk) {
+              const size_t n = std::min(chunk, b - off);
               e = cudaMemcpyAsync(L.buf[tog], j.src[part] + off, n, cudaMemcpyDeviceToHost, L.stream);
               if (e == cudaSuccess) e = cudaEventRecord(L.buf_ev[tog], L.stream);
               if (pend_buf >= 0 && e == cudaSuccess) {
                 e = cudaEventSynchronize(L.buf_ev[pend_buf]);
-                if (e == cudaSuccess) memcpy(j.dst[part] + pend_off, L.buf[pend_buf], pend_n);
+                if (e == cudaSuccess) copy_staged(j.dst[part] + pend_off, L.buf[pend_buf], pend_n, stream);
               }
               pend_buf = tog, pend_off = off, pend_n = n, tog ^= 1;
             }
             if (pend_buf >= 0 && e == cudaSuccess) {
               e = cudaEventSynchronize(L.buf_ev[pend_buf]);
-              if (e == cudaSuccess) memcpy(j.dst[part] + pend_off, L.buf[pend_buf], pend_n);
+              if (e == cudaSuccess) copy_staged(j.dst[part] + pend_off, L.buf[pend_buf], pend_n, stream);
             }
           }
+          copy_fence();
           if (e != cudaSuccess) err.store((int)e);
           drained[t].store(k + 1, std::memory_order_release);
         }

@@ -531,6 +531,36 @@ def test_extract_host_on_a_sharded_slab(pkg, algo):
     assert np.array_equal(fb, f0) and _bits_equal(vb, v0)
 
 
+@pytest.mark.parametrize("slabs", [1, 3])
+def test_extract_host_never_reads_past_the_field(pkg, monkeypatch, slabs):
+    """The staging copies round a row piece up to the staged pitch; the last row must still be read exactly.  The field
+    ends on the last byte before an inaccessible page: one byte too far kills the process."""
+    import ctypes, mmap
+    shape = (70, 33, 41)  # 70 samples per row: the staged pitch (72) is wider than the row
+    s = np.asfortranarray(pkg.synth.gyroid(shape))
+    nbytes, page = s.nbytes, mmap.PAGESIZE
+    span = (nbytes + page - 1) // page * page
+    mm = mmap.mmap(-1, span + page)
+    base = ctypes.addressof(ctypes.c_char.from_buffer(mm))
+    libc = ctypes.CDLL(None, use_errno=True)
+    libc.mprotect.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    assert libc.mprotect(base + span, page, 0) == 0  # PROT_NONE
+    try:
+        a = np.frombuffer(mm, dtype=np.float32, count=s.size, offset=span - nbytes).reshape(shape, order="F")
+        a[...] = s
+        assert a.ctypes.data + nbytes == base + span
+        m = _method(pkg, "MC", 0.0, True)
+        v0, f0 = pkg.api.isosurface_two_phase(s, m)
+        monkeypatch.setenv("B200ISO_HOST_SLABS", str(slabs))
+        p = pkg.api.make_params(m)
+        vb, fb = np.empty((len(v0), 3), np.float32), np.empty((len(f0), 3), np.int64)
+        nv, nf, _, fits = pkg.api.get_handle(0).extract_host(p, a.ctypes.data, *shape, shape[0], vb.ctypes.data, len(vb), fb.ctypes.data, len(fb))
+        assert fits and np.array_equal(fb, f0) and _bits_equal(vb, v0)
+        del a
+    finally:
+        libc.mprotect(base + span, page, 3)
+
+
 @pytest.mark.parametrize("algo", ["MC", "MT"])
 def test_host_paths_pinned_and_pageable_arrays(pkg, algo):
     """Pinned caller arrays take the direct-DMA lanes, pageable ones the threaded pinned staging (several 8 MB chunks

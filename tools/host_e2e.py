@@ -25,6 +25,17 @@ def timeit(name, fn, k=4):
 
 v, f = pkg.isosurface(hf, m)
 nv, nf = len(v), len(f)
+if len(sys.argv) > 2 and sys.argv[2] == "sweep":
+    # usage: host_e2e.py 1024 sweep "A=1 B=2" "A=3" ...: the public call under each environment, in one process
+    # (the library reads its B200ISO_HOST_* knobs per call)
+    for cfg in sys.argv[3:]:
+        kv = dict(x.split("=") for x in cfg.split())
+        os.environ.update(kv)
+        timeit(f"isosurface(pageable) [{cfg}]", lambda: pkg.isosurface(hf, m), k=5)
+        timeit(f"  upload + count only     [{cfg}]", lambda: h.extract_host(p, hf.ctypes.data, n, n, n, n, 0, 0, 0, 0), k=3)
+        for k_ in kv:
+            del os.environ[k_]
+    sys.exit(0)
 timeit("public isosurface(pageable), fresh output arrays every call", lambda: pkg.isosurface(hf, m))
 pv, pf = np.empty((nv + 1024, 3), np.float32), np.empty((nf + 1024, 3), np.int64)
 pv[:] = 0; pf[:] = 0
