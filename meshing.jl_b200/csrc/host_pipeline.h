@@ -219,8 +219,21 @@ struct Uploader {
               e = (w == spitch && w == dp) ? cudaMemcpyAsync(sb.dst + r0 * dp, src + r0 * spitch, (r1 - r0) * w, cudaMemcpyHostToDevice, L.stream)
                                            : cudaMemcpy2DAsync(sb.dst + r0 * dp, dp, src + r0 * spitch + xo, spitch, w, r1 - r0,
                                                                cudaMemcpyHostToDevice, L.stream);
+            } else if (dp > chunk) {
+              // a row piece longer than a chunk (millions of samples along x): the row goes up in chunk-sized segments
+              for (size_t r = r0; r < r1 && e == cudaSuccess; ++r)
+                for (size_t off = 0; off < w && e == cudaSuccess; off += chunk) {
+                  const size_t nb = std::min(chunk, w - off);
+                  e = cudaEventSynchronize(L.buf_ev[tog]);
+                  if (e != cudaSuccess) break;
+                  copy_staged(L.buf[tog], src + r * spitch + xo + off, nb, stream);
+                  copy_fence();
+                  e = cudaMemcpyAsync(sb.dst + r * dp + off, L.buf[tog], nb, cudaMemcpyHostToDevice, L.stream);
+                  if (e == cudaSuccess) e = cudaEventRecord(L.buf_ev[tog], L.stream);
+                  tog ^= 1;
+                }
             } else {
-              const size_t per = std::max<size_t>(1, chunk / dp);
+              const size_t per = chunk / dp;  // (>= 1)
               for (size_t r = r0; r < r1 && e == cudaSuccess; r += per) {
                 const size_t n = std::min(per, r1 - r);
                 e = cudaEventSynchronize(L.buf_ev[tog]);  // the chunk's previous DMA has drained

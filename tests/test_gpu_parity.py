@@ -531,6 +531,21 @@ def test_extract_host_on_a_sharded_slab(pkg, algo):
     assert np.array_equal(fb, f0) and _bits_equal(vb, v0)
 
 
+@pytest.mark.parametrize("slabs", [1, 2])
+def test_extract_host_rows_longer_than_a_staging_chunk(pkg, oracle, monkeypatch, slabs):
+    """A pageable field whose rows exceed one pinned staging chunk goes up in segments (the chunk is shrunk to 64 KB so
+    that 80 KB rows do what 2.4 MB rows do by default)."""
+    s = pkg.synth.noise((20011, 5, 4))
+    m = _method(pkg, "MC", 0.0, True)
+    vo, fo = oracle.isosurface(s, ALGOS["MC"], iso=0.0, iso_is_f32=True, eps_is_f32=True)
+    monkeypatch.setenv("B200ISO_HOST_CHUNK_KB", "64")
+    monkeypatch.setenv("B200ISO_HOST_SLABS", str(slabs))
+    v1, f1 = pkg.isosurface(s, m, capacity=(len(vo) + 1, len(fo) + 1))
+    assert np.array_equal(f1, fo) and _bits_equal(v1, vo)
+    v2, f2 = pkg.api.isosurface_two_phase(s, m)
+    assert np.array_equal(f2, fo) and _bits_equal(v2, vo)
+
+
 @pytest.mark.parametrize("slabs", [1, 3])
 def test_extract_host_never_reads_past_the_field(pkg, monkeypatch, slabs):
     """The staging copies round a row piece up to the staged pitch; the last row must still be read exactly.  The field
