@@ -434,6 +434,28 @@ __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* s_
   return base + inc - v;
 }
 
+// the same over 64-bit values (two packed 32-bit scans in one pass); s_w: CB_THREADS / 32 words
+__device__ __forceinline__ unsigned long long block_excl_scan_u64(unsigned long long v, unsigned long long* s_w, unsigned long long& total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned long long inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) s_w[w] = inc;
+  __syncthreads();
+  unsigned long long base = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < CB_THREADS / 32; ++i) {
+    const unsigned long long t = s_w[i];
+    if (i < w) base += t;
+    tot += t;
+  }
+  total = tot;
+  return base + inc - v;
+}
 
 // ------------------------------------------------------------------------------------------------------
 // decoupled look-back scan state: one 16-byte entry per block, {nverts, nfaces}, each word
@@ -676,6 +698,13 @@ __device__ __forceinline__ void mc_interp(const GenArgs& a, float va, float vb, 
   }
 }
 constexpr int GEN_NB = 2 * CB_THREADS;  // active voxels per dense round (two records per thread)
+#ifndef ISO_GEN_SPLIT
+#define ISO_GEN_SPLIT 1
+#endif
+// Which two records of a round a thread takes: t and t + 128 (SPLIT) or 2t and 2t + 1.  A typical block has ~155
+// records: with pairs only threads 0..77 gather samples while the fourth warp waits at the barrier; split, every warp
+// holds a record per lane and the few records beyond 128 fall to the first warp.
+constexpr bool GEN_SPLIT = ISO_GEN_SPLIT != 0;
 constexpr int GEN_MAXV = GEN_NB * 12;   // vertices of a round (MC: <= 12 per voxel)
 constexpr int GEN_MAXF = GEN_NB * 5;    // faces of a round (MC: <= 5 per voxel)
 
@@ -793,6 +822,7 @@ template <int MODE, typename V, bool KEYS = false>
 __global__ void __launch_bounds__(CB_THREADS, ISO_GEN_MINB)
 mc_generate_kernel(GenArgs a, Grid g) {
   __shared__ uint32_t s_w[CB_THREADS / 32];
+  __shared__ unsigned long long s_w64[CB_THREADS / 32];
   __shared__ __align__(16) uint4 rec[GEN_NB];
   __shared__ unsigned long long recf[GEN_NB];
   using T = typename FieldOf<MODE>::type;  // Float32, or Float64 for MODE 3
@@ -802,19 +832,13 @@ mc_generate_kernel(GenArgs a, Grid g) {
   const int tid = threadIdx.x;
   const unsigned b = blockIdx.x;
   if (a.abort_flag && *a.abort_flag) return;  // the exchange that was to deliver the vertex base failed
-  unsigned long long bv, bf;
-  {
-    // the count left every block's exclusive prefix: a block whose successor starts at the same vertex has
-    // no active voxel (each one emits >= 3 vertices) -- leave before touching the bit-field.  On sparse fields
-    // (a few shapes in a big volume) that is most blocks.
-    bv = a.woff[2 * (unsigned long long)b];
-    const unsigned long long v1 = (long long)b + 1 < a.nblocks ? a.woff[2 * ((unsigned long long)b + 1)] : (unsigned long long)a.totals_a[0];
-    if (bv == v1) return;
-    bf = a.woff[2 * (unsigned long long)b + 1];
-  }
-  // The count left the block's active-voxel records (scan order) unless there are more than REC_CAP of them: then
-  // (dense fields) this block derives them from the bit-field itself (A + B1a below).
+  // The count left the block's number of active voxels and (unless there are more than REC_CAP of them: dense fields,
+  // which take this kernel's own front end, A + B1a below) their records in scan order.  A block without active voxels
+  // leaves on that one word, before touching anything else; on sparse fields (a few shapes in a big volume) that is
+  // most blocks.  The block's prefix (woff) is not needed before the first store: its loads overlap the record loads.
   const uint32_t nrec = __ldg(a.nrecs + b);
+  if (nrec == 0) return;
+  unsigned long long bv = a.woff[2 * (unsigned long long)b], bf = a.woff[2 * (unsigned long long)b + 1];
   const bool from_recs = nrec <= (uint32_t)g.rec_cap;  // (uniform over the block)
   TMap tm;
   tm.x = (int)fast_div(b, g.bpr_mul, g.bpr_sh);
@@ -856,13 +880,20 @@ mc_generate_kernel(GenArgs a, Grid g) {
     // z-adjacent records (same column, z + 1: adjacent in scan order) share a sample plane: the lower plane of the
     // second is the upper plane of the first -- taken from registers (in-thread pair) or from the lane below
     // (shuffle) instead of being gathered again.
-    const uint32_t r0 = 2 * tid, r1 = r0 + 1;
+    const uint32_t r0 = GEN_SPLIT ? (uint32_t)tid : 2u * tid, r1 = GEN_SPLIT ? (uint32_t)tid + CB_THREADS : r0 + 1;
     uint32_t nvf0 = 0, nvf1 = 0;  // vertices | faces << 16 of the two records
     uint32_t yz0 = 0xffffffffu, yz1 = 0xfffffffeu;
     uint2 rc0 = make_uint2(0, 0), rc1 = make_uint2(0, 0);  // (y | z << 16, case) of the two records
     if (from_recs) {
-      // the count's records: case | voxel-in-quad-cell << 8 | quad-cell-in-block << 15 (one aligned 8-byte load per thread)
-      const uint2 w = r0 < cnt ? __ldg(reinterpret_cast<const uint2*>(a.recs + (unsigned long long)b * (unsigned)g.rec_cap + lo + r0)) : make_uint2(0, 0);
+      // the count's records: case | voxel-in-quad-cell << 8 | quad-cell-in-block << 15
+      const uint32_t* rp = a.recs + (unsigned long long)b * (unsigned)g.rec_cap + lo;
+      uint2 w = make_uint2(0, 0);
+      if constexpr (GEN_SPLIT) {
+        if (r0 < cnt) w.x = __ldg(rp + r0);
+        if (r1 < cnt) w.y = __ldg(rp + r1);
+      } else {
+        if (r0 < cnt) w = __ldg(reinterpret_cast<const uint2*>(rp + r0));  // (one aligned 8-byte load per thread)
+      }
       auto decode = [&](uint32_t wd) {
         const uint32_t qr = q_lo + (wd >> 15), y = fast_div(qr, g.wq_mul, g.wq_sh), zq = qr - y * (uint32_t)g.Wq;
         return make_uint2(y | ((zq * 128u + ((wd >> 8) & 127u)) << 16), wd & 0xffu);
@@ -894,9 +925,11 @@ mc_generate_kernel(GenArgs a, Grid g) {
       const bool vec = sizeof(T) == 4 && a.sdf_vec;
       const int ph = x & 3;
       const T* fld = reinterpret_cast<const T*>(a.sdf) + x;
+      // pairs: r0 continues the z-run of the lane below's r1, r1 continues r0's; split: each continues the lane below's
       const uint32_t pyz1 = __shfl_up_sync(0xffffffffu, yz1, 1);
-      const bool adj0 = lane > 0 && r0 < cnt && yz0 == pyz1 + 0x10000u;  // r0 continues the z-run of the lane below
-      const bool adj1 = r1 < cnt && yz1 == yz0 + 0x10000u;                // r1 continues r0's run
+      const uint32_t pyz0 = GEN_SPLIT ? __shfl_up_sync(0xffffffffu, yz0, 1) : 0u;
+      const bool adj0 = lane > 0 && r0 < cnt && yz0 == (GEN_SPLIT ? pyz0 : pyz1) + 0x10000u;
+      const bool adj1 = r1 < cnt && (GEN_SPLIT ? (lane > 0 && yz1 == pyz1 + 0x10000u) : yz1 == yz0 + 0x10000u);
       Plane<T> L0{}, U0{}, L1{}, U1{};
       if (r0 < cnt) {
         const T* p = fld + g.ldx * (long long)(yz0 & 0xffffu) + g.plane * (long long)(yz0 >> 16);
@@ -908,16 +941,39 @@ mc_generate_kernel(GenArgs a, Grid g) {
         if (!adj1) L1 = load_plane<T>(p, g.ldx, ph, vec);
         U1 = load_plane<T>(p + g.plane, g.ldx, ph, vec);
       }
-      const Plane<T> below = shfl_up_plane<T>(U1);  // (all lanes take part)
-      if (adj0) L0 = below;
-      if (adj1) L1 = U0;
+      if constexpr (GEN_SPLIT) {
+        const Plane<T> below0 = shfl_up_plane<T>(U0);  // (all lanes take part)
+        if (adj0) L0 = below0;
+        if ((uint32_t)(tid & ~31) + CB_THREADS < cnt) {  // (uniform over the warp: some lane has a second record)
+          const Plane<T> below1 = shfl_up_plane<T>(U1);
+          if (adj1) L1 = below1;
+        }
+      } else {
+        const Plane<T> below = shfl_up_plane<T>(U1);  // (all lanes take part)
+        if (adj0) L0 = below;
+        if (adj1) L1 = U0;
+      }
       // MC corner order (src/marching_cubes.jl:42-49): 0 (0,0,0) 1 (1,0,0) 2 (1,1,0) 3 (0,1,0), then the same at z + 1.
       // A thread's two records are 4 chunks of 16 bytes; chunk c of thread t lives at chunk c ^ ((t >> 1) & 3) of the
       // thread's 64 bytes, so that the 8 lanes of a quarter-warp hit 8 different bank groups (unswizzled: 4-way conflicts).
       {
-        float4* crow = reinterpret_cast<float4*>(&corner[r0][0]);  // (T = double: 8 chunks of 16 bytes, same rule on pairs)
-        const int sw = (tid >> 1) & 3;
-        if constexpr (sizeof(T) == 4) {
+        if constexpr (sizeof(T) == 4 && GEN_SPLIT) {
+          // a record is 2 chunks of 16 bytes; chunk c of record r lives at chunk c ^ ((r >> 2) & 1) of its 32 bytes:
+          // the 8 lanes of a quarter-warp (rows 32 bytes apart) then hit 8 different bank groups
+          const int sw = (tid >> 2) & 1;  // (the same for r0 and r1 = r0 + 128)
+          if (r0 < cnt) {
+            float4* crow = reinterpret_cast<float4*>(&corner[r0][0]);
+            crow[0 ^ sw] = make_float4(L0.a00, L0.a10, L0.a11, L0.a01);
+            crow[1 ^ sw] = make_float4(U0.a00, U0.a10, U0.a11, U0.a01);
+          }
+          if (r1 < cnt) {
+            float4* crow = reinterpret_cast<float4*>(&corner[r1][0]);
+            crow[0 ^ sw] = make_float4(L1.a00, L1.a10, L1.a11, L1.a01);
+            crow[1 ^ sw] = make_float4(U1.a00, U1.a10, U1.a11, U1.a01);
+          }
+        } else if constexpr (sizeof(T) == 4) {
+          float4* crow = reinterpret_cast<float4*>(&corner[r0][0]);  // (T = double: 8 chunks of 16 bytes, same rule on pairs)
+          const int sw = (tid >> 1) & 3;
           if (r0 < cnt) {
             crow[0 ^ sw] = make_float4(L0.a00, L0.a10, L0.a11, L0.a01);
             crow[1 ^ sw] = make_float4(U0.a00, U0.a10, U0.a11, U0.a01);
@@ -938,20 +994,31 @@ mc_generate_kernel(GenArgs a, Grid g) {
         }
       }
     }
-    uint32_t wtot;
-    const uint32_t ex = block_excl_scan_u32(nvf0 + nvf1, s_w, wtot);
+    // local offsets in record order: pairs -- one scan of the pair sums; split -- records 0..127 then 128..255, both
+    // scans in one 64-bit pass
+    uint32_t wtot, ex0, ex1;
+    if constexpr (GEN_SPLIT) {
+      unsigned long long tot64;
+      const unsigned long long ex64 = block_excl_scan_u64((unsigned long long)nvf0 | ((unsigned long long)nvf1 << 32), s_w64, tot64);
+      ex0 = (uint32_t)ex64, ex1 = (uint32_t)tot64 + (uint32_t)(ex64 >> 32);
+      wtot = (uint32_t)tot64 + (uint32_t)(tot64 >> 32);
+    } else {
+      ex0 = block_excl_scan_u32(nvf0 + nvf1, s_w, wtot);
+      ex1 = ex0 + nvf0;
+    }
     {
-      const uint32_t v0 = ex & 0xffffu, f0 = ex >> 16;
       const uint32_t nv0 = nvf0 & 0xffffu, nf0 = nvf0 >> 16, nv1 = nvf1 & 0xffffu, nf1 = nvf1 >> 16;
       if (r0 < cnt) {
-        rec[r0].y = ex;  // local vertex offset | local face offset << 16
+        rec[r0].y = ex0;  // local vertex offset | local face offset << 16
+        const uint32_t v0 = ex0 & 0xffffu, f0 = ex0 >> 16;
         for (uint32_t i = 0; i < nv0; ++i) owner_v[v0 + i] = (uint8_t)r0;
         for (uint32_t i = 0; i < nf0; ++i) owner_f[f0 + i] = (uint8_t)r0;
       }
       if (r1 < cnt) {
-        rec[r1].y = ex + nvf0;
-        for (uint32_t i = 0; i < nv1; ++i) owner_v[v0 + nv0 + i] = (uint8_t)r1;
-        for (uint32_t i = 0; i < nf1; ++i) owner_f[f0 + nf0 + i] = (uint8_t)r1;
+        rec[r1].y = ex1;
+        const uint32_t v1 = ex1 & 0xffffu, f1 = ex1 >> 16;
+        for (uint32_t i = 0; i < nv1; ++i) owner_v[v1 + i] = (uint8_t)r1;
+        for (uint32_t i = 0; i < nf1; ++i) owner_f[f1 + i] = (uint8_t)r1;
       }
     }
     const uint32_t nvr = wtot & 0xffffu, nfr = wtot >> 16;
@@ -980,9 +1047,15 @@ mc_generate_kernel(GenArgs a, Grid g) {
       }
       T va, vb;
       if constexpr (sizeof(T) == 4) {  // (chunk swizzle of the corner store, see B1b)
-        const T* cp = &corner[s & ~1u][0];
-        const uint32_t sw = (s >> 2) & 3u, hb = 2u * (s & 1u);
-        va = cp[(((hb + (ca >> 2)) ^ sw) << 2) + (ca & 3u)], vb = cp[(((hb + (cb >> 2)) ^ sw) << 2) + (cb & 3u)];
+        if constexpr (GEN_SPLIT) {
+          const T* cp = &corner[s][0];
+          const uint32_t sw = (s >> 2) & 1u;
+          va = cp[(((ca >> 2) ^ sw) << 2) + (ca & 3u)], vb = cp[(((cb >> 2) ^ sw) << 2) + (cb & 3u)];
+        } else {
+          const T* cp = &corner[s & ~1u][0];
+          const uint32_t sw = (s >> 2) & 3u, hb = 2u * (s & 1u);
+          va = cp[(((hb + (ca >> 2)) ^ sw) << 2) + (ca & 3u)], vb = cp[(((hb + (cb >> 2)) ^ sw) << 2) + (cb & 3u)];
+        }
       } else {
         va = corner[s][ca], vb = corner[s][cb];
       }
