@@ -113,6 +113,7 @@ struct b200iso_handle {
   DevBuf<unsigned int> ride;
   long long ride_ny = -1, ride_tpr = -1, ride_nbi = -1;  // shape the cumulative row counters belong to
   unsigned int ride_step = 0;
+  long long ride_min_tasks = 8192;  // counting warps ride only in classify kernels of at least this many tasks (env B200ISO_RIDE_MIN_TASKS: tests)
   int ride_stop = iso::TM_WARPS * iso::SP_ZW * 3 / 4;  // counting warps stop claiming at 3/4 of the CTA's classify work (env B200ISO_RIDE_STOP: z-words of 64)
   int ride_warps = 6;  // counting warps per TMA classify CTA (0 = separate count kernel only; b200iso_set_ride_warps, env B200ISO_RIDE)
   // grid coordinates are a function of the call's shape and ranges only: recomputed when those change
@@ -271,7 +272,7 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
       cr.g = g;
       // (only when the classify kernel runs for many waves of CTAs: on a 129-plane slab -- 4096 tasks, 3.5 waves -- the
       // rows complete too late for the riding warps to get anything done, and they only cost: 0.139 vs 0.122 ms)
-      if (!mt && h->ride_warps > 0 && ntasks >= 8192) {
+      if (h->ride_warps > 0 && ntasks >= h->ride_min_tasks) {
         const long long nbi = g.blocks_per_row;
         const size_t words = (size_t)iso::RIDE_HDR + (size_t)nbi + (size_t)ny;
         if (int rc = h->ride.reserve(words)) return rc;
@@ -285,11 +286,16 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
         cr.rows_done = cr.next_x + nbi;
         cr.target = ++h->ride_step * (unsigned int)tpr;
         cr.stop_at = h->ride_stop;
+        cr.celloff = mt ? h->celloff.p : nullptr;
         ride = true;
       }
       const unsigned tb = (unsigned)((ntasks + iso::TM_WARPS - 1) / iso::TM_WARPS);
-      iso::signpack_tma_kernel<<<tb, (iso::TM_WARPS + (ride ? h->ride_warps : 0)) * 32, iso::TM_SMEM, st>>>(tmap, h->bits.p, g.nx, g.ny, g.nz, g.W, thr, nxseg, nzc,
-                                                                                                  ntasks, h->chain.p, nclear, cr);
+      if (mt && ride)
+        iso::signpack_tma_kernel<true><<<tb, (iso::TM_WARPS + std::min(h->ride_warps, iso::TM_CNT_WARPS_MT)) * 32, iso::TM_SMEM, st>>>(
+            tmap, h->bits.p, g.nx, g.ny, g.nz, g.W, thr, nxseg, nzc, ntasks, h->chain.p, nclear, cr);
+      else
+        iso::signpack_tma_kernel<false><<<tb, (iso::TM_WARPS + (ride ? h->ride_warps : 0)) * 32, iso::TM_SMEM, st>>>(
+            tmap, h->bits.p, g.nx, g.ny, g.nz, g.W, thr, nxseg, nzc, ntasks, h->chain.p, nclear, cr);
       h->classify_path = B200ISO_CLASSIFY_TMA;
     } else if (vec) {
       iso::signpack_kernel<true, float><<<nb, iso::SP_WARPS * 32, 0, st>>>(sdf_f, h->bits.p, g.nx, g.ny, g.nz, g.ldx, g.W, thr, nxseg, ntasks, h->chain.p, nclear);
@@ -315,15 +321,24 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
     unsigned ncb = (unsigned)((h->nblocks + iso::WC_THREADS / 32 - 1) / (iso::WC_THREADS / 32));
     if (ride) ncb = std::max(1u, std::min(ncb, std::max(148u * 4u, ncb / 4)));
     static_assert(iso::RIDE_HDR_WORDS == iso::RIDE_HDR, "ride buffer layout");
-    iso::mc_count_chunks_kernel<<<ncb, iso::WC_THREADS, 0, st>>>(h->bits.p, g, h->nblocks, h->woff.p, h->recs.p, h->nrecs.p, ride ? h->ride.p : nullptr);
+    iso::mc_count_chunks_kernel<false><<<ncb, iso::WC_THREADS, 0, st>>>(h->bits.p, g, h->nblocks, h->woff.p, h->recs.p, h->nrecs.p,
+                                                                        ride ? h->ride.p : nullptr, nullptr);
     CU(cudaGetLastError());
     iso::mc_scan_chunks_kernel<<<(unsigned)nsb, iso::SC_THREADS, 0, st>>>(h->woff.p, h->nblocks, chain, ticket, nsb, h->totals_dev, totals_out,
                                                                           ride ? h->ride.p : nullptr, ride ? iso::RIDE_HDR + g.blocks_per_row : 0);
   } else {
-    iso::mt_count_kernel<<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->celloff.p, h->woff.p, h->recs.p, h->nrecs.p);
+    if (ride) {  // what the counting warps left (the y-blocks of the last rows), a warp per generate block
+      unsigned ncb = (unsigned)((h->nblocks + iso::WC_THREADS / 32 - 1) / (iso::WC_THREADS / 32));
+      ncb = std::max(1u, std::min(ncb, std::max(148u * 4u, ncb / 4)));
+      iso::mc_count_chunks_kernel<true><<<ncb, iso::WC_THREADS, 0, st>>>(h->bits.p, g, h->nblocks, h->woff.p, h->recs.p, h->nrecs.p, h->ride.p,
+                                                                         h->celloff.p);
+    } else {
+      iso::mt_count_kernel<<<(unsigned)h->nblocks, iso::CB_THREADS, 0, st>>>(h->bits.p, g, h->celloff.p, h->woff.p, h->recs.p, h->nrecs.p);
+    }
     CU(cudaGetLastError());
     iso::mt_scan_blocks_kernel<<<(unsigned)nsb, iso::SC_THREADS, 0, st>>>(h->woff.p, h->nblocks, h->status.p, chain, ticket, nsb,
-                                                                          g.ghost ? (long long)g.blocks_per_row - 1 : -1LL, ghost_words, h->totals_dev, totals_out);
+                                                                          g.ghost ? (long long)g.blocks_per_row - 1 : -1LL, ghost_words, h->totals_dev, totals_out,
+                                                                          ride ? h->ride.p : nullptr, ride ? iso::RIDE_HDR + g.blocks_per_row : 0);
   }
   CU(cudaGetLastError());
   h->launches += 2;
@@ -406,9 +421,11 @@ const char* b200iso_last_error(void) { return g_err; }
 static int create_impl(b200iso_handle* h) {
   if (const char* e = getenv("B200ISO_TMA")) h->tma_mode = atoi(e) != 0 ? 1 : 0;
   if (const char* e = getenv("B200ISO_RIDE_STOP")) h->ride_stop = atoi(e);
+  if (const char* e = getenv("B200ISO_RIDE_MIN_TASKS")) h->ride_min_tasks = std::max(1ll, atoll(e));
   if (const char* e = getenv("B200ISO_RIDE")) h->ride_warps = std::max(0, std::min(iso::TM_CNT_WARPS_MAX, atoi(e)));
   // per device: the TMA classify kernel needs more than the default 48 KB of dynamic shared memory
-  CU(cudaFuncSetAttribute(iso::signpack_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iso::TM_SMEM));
+  CU(cudaFuncSetAttribute(iso::signpack_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iso::TM_SMEM));
+  CU(cudaFuncSetAttribute(iso::signpack_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iso::TM_SMEM));
   CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
   CU(cudaMalloc((void**)&h->totals_dev, 4 * sizeof(long long)));

@@ -86,8 +86,82 @@ mt_count_kernel(const uint32_t* __restrict__ bits, Grid g, uint32_t* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Marching Cubes count, warp-autonomous: a warp walks one generate block's quad-cells (lane <-> quad-cell,
-// 32 at a time) and stores the block's raw (vertex, face) pair -- no chain, no ticket, no barrier.
+// Count, warp-autonomous: a warp walks one generate block's quad-cells (lane <-> quad-cell, 32 at a time) and stores
+// the block's raw (vertex, face) pair -- no chain, no ticket, no barrier.  The Marching Cubes form is mc_count_chunk
+// (iso_kernels.cuh); this is the Marching Tetrahedra form of mt_count_kernel above -- same records, same celloff, same
+// totals -- used by the counting warps inside the TMA classify kernel and by the kernel that takes what they left.
+template <bool CG>
+__device__ __forceinline__ void mt_count_chunk(const uint32_t* __restrict__ bits, const Grid& g, long long chunk, const uint8_t* nf_s,
+                                               uint32_t* __restrict__ celloff, uint32_t* __restrict__ recs, uint32_t* __restrict__ nrecs,
+                                               uint32_t& nv_out, uint32_t& nf_out) {
+  const int lane = threadIdx.x & 31;
+  uint32_t nf = 0, base = 0, vbase = 0;  // records / vertices of the block before this group of 32 quad-cells (uniform)
+  const int x = (int)(chunk / g.blocks_per_row);
+  const int q_lo = (int)(chunk - (long long)x * g.blocks_per_row) * CB_THREADS;
+  uint32_t* rec = recs + chunk * g.rec_cap;
+  const int fx = (x + g.xoff) == 0 ? 1 : 0;  // low-boundary flags use GLOBAL x
+  for (int q0 = q_lo; q0 < q_lo + CB_THREADS && q0 < g.quads_per_row; q0 += 32) {
+    const int qr = q0 + lane;
+    const bool live = qr < g.quads_per_row;
+    const int y = (int)fast_div((unsigned)qr, g.wq_mul, g.wq_sh), zq = qr - y * g.Wq;
+    Quad q;
+    const bool act = live && load_quad<CG>(bits, g, x, y, zq, q);
+    uint32_t mm[4] = {0, 0, 0, 0}, na = 0, cv[4] = {0, 0, 0, 0}, mynv = 0, e0 = vbase;
+    if (act) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mm[i] = active_mask(q, i), na += __popc(mm[i]);
+    }
+    if (__any_sync(0xffffffffu, na != 0)) {  // (uniform)
+      uint32_t inc = na;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      uint32_t pos = base + inc - na;
+      base += __shfl_sync(0xffffffffu, inc, 31);
+      if (na) {
+        const int fxy = fx | (y == 0 ? 2 : 0);
+        const uint32_t qtag = (uint32_t)(qr - q_lo) << 15;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t m = mm[i];
+          if (m) {
+            cv[i] = mt_owned_masked(q, i, q.vm[i], fxy, zq == 0 && i == 0);
+            mynv += cv[i];
+            while (m) {
+              const int k = __ffs(m) - 1;
+              m &= m - 1;
+              const uint32_t c = case_of<1>(q, i, k);
+              nf += nf_s[c];
+              if (pos < (uint32_t)g.rec_cap) rec[pos] = c | ((uint32_t)(i * 32 + k) << 8) | qtag;
+              ++pos;
+            }
+          }
+        }
+      }
+      // in-block exclusive vertex prefix of every cell (lane order == scan order)
+      uint32_t vinc = mynv;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, vinc, o);
+        if (lane >= o) vinc += t;
+      }
+      e0 = vbase + vinc - mynv;
+      vbase += __shfl_sync(0xffffffffu, vinc, 31);
+    }
+    if (live) {
+      uint4 o;
+      o.x = e0, o.y = e0 + cv[0], o.z = o.y + cv[1], o.w = o.z + cv[2];
+      *reinterpret_cast<uint4*>(celloff + (long long)x * g.row_words + (long long)y * g.W + zq * 4) = o;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nf += __shfl_xor_sync(0xffffffffu, nf, o);
+  if (lane == 0) nrecs[chunk] = base;
+  nv_out = vbase, nf_out = nf;
+}
+
 constexpr int WC_THREADS = 256;  // 8 warps = 8 generate blocks per counting block
 
 // ride: the counting warps inside the TMA classify kernel (signpack_tma.cuh) have already counted every y-block
@@ -95,22 +169,26 @@ constexpr int WC_THREADS = 256;  // 8 warps = 8 generate blocks per counting blo
 // rest with a grid-stride loop (everything, starting at item 0, when ride == nullptr).  Items are numbered
 // y-block-major: item = bi * nxv + x.
 constexpr int RIDE_HDR_WORDS = 32;  // == RIDE_HDR of signpack_tma.cuh: cur_bi, statistics, then next_x[]
+// MT = true: the Marching Tetrahedra count (celloff is written as well), what the counting warps left of it.
+template <bool MT>
 __global__ void __launch_bounds__(WC_THREADS, 4)
 mc_count_chunks_kernel(const uint32_t* __restrict__ bits, Grid g, long long nchunks, unsigned long long* __restrict__ woff,
-                       uint32_t* __restrict__ recs, uint32_t* __restrict__ nrecs, const unsigned int* __restrict__ ride) {
+                       uint32_t* __restrict__ recs, uint32_t* __restrict__ nrecs, const unsigned int* __restrict__ ride,
+                       uint32_t* __restrict__ celloff) {
   __shared__ uint8_t nf_s[256];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long nxv = g.nx - 1;
   const long long first = ride ? (long long)__ldg(ride) * nxv : 0ll;
   if (first + (long long)blockIdx.x * (WC_THREADS / 32) >= nchunks) return;  // (uniform over the block)
-  nf_s[threadIdx.x] = (uint8_t)((ISO_MC_VERTS[threadIdx.x] >> 52) & 7);
+  nf_s[threadIdx.x] = MT ? ISO_MT_NF[threadIdx.x] : (uint8_t)((ISO_MC_VERTS[threadIdx.x] >> 52) & 7);
   __syncthreads();
   for (long long item = first + (long long)blockIdx.x * (WC_THREADS / 32) + w; item < nchunks; item += (long long)gridDim.x * (WC_THREADS / 32)) {
     const long long bi = item / nxv, x = item - bi * nxv;
     if (ride && x < (long long)__ldg(ride + RIDE_HDR_WORDS + bi)) continue;  // counted inside the classify kernel
     const long long chunk = x * g.blocks_per_row + bi;
     uint32_t nv, nf;
-    mc_count_chunk<false>(bits, g, chunk, nf_s, recs, nrecs, nv, nf);
+    if constexpr (MT) mt_count_chunk<false>(bits, g, chunk, nf_s, celloff, recs, nrecs, nv, nf);
+    else mc_count_chunk<false>(bits, g, chunk, nf_s, recs, nrecs, nv, nf);
     if (lane == 0) woff[2 * chunk] = nv, woff[2 * chunk + 1] = nf;
   }
 }
@@ -185,10 +263,16 @@ mc_scan_chunks_kernel(unsigned long long* __restrict__ woff, long long nchunks, 
 __global__ void __launch_bounds__(SC_THREADS)
 mt_scan_blocks_kernel(const unsigned long long* __restrict__ raw, long long nblocks, unsigned long long* status,
                       unsigned long long* chain, unsigned int* ticket, long long nsb, long long ghost_block,
-                      unsigned long long* ghost_words, long long* totals_a, long long* totals_b) {
+                      unsigned long long* ghost_words, long long* totals_a, long long* totals_b, unsigned int* ride, int nride) {
   __shared__ unsigned long long wsum_v[SC_THREADS / 32], wsum_f[SC_THREADS / 32];
   __shared__ unsigned long long base_s[2];
   __shared__ unsigned sb;
+  if (ride && blockIdx.x == 0) {  // the counting warps' queues are empty again for the next step (as in mc_scan_chunks_kernel)
+    if (threadIdx.x == 0) ride[2] = ride[1];
+    __syncthreads();
+    for (int i = threadIdx.x; i < nride; i += SC_THREADS)
+      if (i != 2) ride[i] = 0u;
+  }
   if (threadIdx.x == 0) sb = atomicAdd(ticket, 1u);
   __syncthreads();
   const long long b = sb;

@@ -9,7 +9,7 @@
 #pragma once
 #include <cuda.h>
 
-#include "iso_kernels.cuh"
+#include "count_kernel.cuh"
 
 namespace iso {
 
@@ -91,6 +91,7 @@ struct CountRide {
   unsigned int* rows_done;     // [ny] finished classify tasks per sample row, cumulative over steps
   unsigned int target;         // rows_done[y] >= target  <=>  row y is complete in this step
   int stop_at;                 // counting warps stop claiming once the CTA's classify warps have finished this many z-words
+  uint32_t* celloff;           // Marching Tetrahedra count (signpack_tma_kernel<true>): in-block vertex prefix of every cell
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -104,9 +105,10 @@ __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
   return v;
 }
 
-// cta_prog: z-words finished by the CTA's classify warps (SP_ZW per warp).  A counting warp that is still counting
+// cta_prog: z-words finished by the CTA's classify warps (ZW per warp, see the kernel).  A counting warp that is still counting
 // when they are through keeps the CTA -- and its 96 KB of shared memory -- from the next classify CTA (measured:
 // classify 0.66 -> 0.72 ms with unbounded claiming), so claiming stops when the classify warps near their end.
+template <bool MT>
 __device__ __forceinline__ void count_ride(const uint32_t* __restrict__ bits, const CountRide& cr, const volatile int* cta_prog,
                                            const uint8_t* nf_s) {
   const int lane = threadIdx.x & 31;
@@ -144,50 +146,58 @@ __device__ __forceinline__ void count_ride(const uint32_t* __restrict__ bits, co
     for (unsigned k = 0; k < n; ++k) {
       const long long chunk = (long long)(x0 + k) * g.blocks_per_row + bi;
       uint32_t nv, nf;
-      mc_count_chunk<true>(bits, g, chunk, nf_s, cr.recs, cr.nrecs, nv, nf);
+      if constexpr (MT) mt_count_chunk<true>(bits, g, chunk, nf_s, cr.celloff, cr.recs, cr.nrecs, nv, nf);
+      else mc_count_chunk<true>(bits, g, chunk, nf_s, cr.recs, cr.nrecs, nv, nf);
       if (lane == 0) cr.woff[2 * chunk] = nv, cr.woff[2 * chunk + 1] = nf;
     }
     if (lane == 0) atomicAdd(cr.head + 1, n);
   }
 }
 
-__global__ void __launch_bounds__((TM_WARPS + TM_CNT_WARPS_MAX) * 32)
+// MT: the counting warps run the Marching Tetrahedra count, which needs more registers than the classify warps' 80: that
+// instantiation is bounded to 6 counting warps and two CTAs per SM (the classify pipeline is sized for two).
+constexpr int TM_CNT_WARPS_MT = 6;
+// (Tasks of 8 or 4 z-words instead of 16 -- more, shorter tasks, so that the counting warps also find rows to follow on
+// 512^3 grids and 129-plane slabs -- were measured and lost: 512^3 classify 0.093 -> 0.128 ms for 0.021 ms less count.)
+template <bool MT>
+__global__ void __launch_bounds__((TM_WARPS + (MT ? TM_CNT_WARPS_MT : TM_CNT_WARPS_MAX)) * 32, MT ? 2 : 0)
 signpack_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t* __restrict__ bits, int nx, int ny, int nz, int W,
                     float thresh, int nxseg, int nzc, long long ntasks, unsigned long long* __restrict__ clear, int nclear,
                     const __grid_constant__ CountRide cr) {
   extern __shared__ __align__(128) unsigned char tm_smem[];
   __shared__ __align__(8) uint64_t full[TM_WARPS][TM_STAGES];
   __shared__ uint8_t nf_s[256];
-  __shared__ int cta_prog;  // z-words finished by the classify warps of this CTA (SP_ZW each)
+  constexpr int ZW = SP_ZW, NBOXES = TM_BOXES;  // z-words and boxes per task
+  __shared__ int cta_prog;  // z-words finished by the classify warps of this CTA (ZW each)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   // block 0 resets the scan state (ticket + look-back chain) of the count/scan kernels that follow in the stream
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < nclear; i += blockDim.x) clear[i] = 0ull;
   if (threadIdx.x == 0) cta_prog = 0;
   if (cr.nbi > 0)
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) nf_s[i] = (uint8_t)((ISO_MC_VERTS[i] >> 52) & 7);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) nf_s[i] = MT ? ISO_MT_NF[i] : (uint8_t)((ISO_MC_VERTS[i] >> 52) & 7);
   __syncthreads();
   if (wib >= TM_WARPS) {  // ---- counting warps ----
-    if (cr.nbi > 0) count_ride(bits, cr, &cta_prog, nf_s);
+    if (cr.nbi > 0) count_ride<MT>(bits, cr, &cta_prog, nf_s);
     return;
   }
   // ---- classify warps ----
   const long long task = (long long)blockIdx.x * TM_WARPS + wib;
   if (task >= ntasks) {
-    if (lane == 0) atomicAdd(&cta_prog, SP_ZW);
+    if (lane == 0) atomicAdd(&cta_prog, ZW);
     return;
   }
   unsigned char* base = tm_smem + (128 - (smem_u32(tm_smem) & 127)) % 128 + (size_t)wib * TM_SMEM_PER_WARP;
   float* box = reinterpret_cast<float*>(base);                                                      // [TM_STAGES][TM_BZ][128]
-  uint32_t* wstage = reinterpret_cast<uint32_t*>(base + (size_t)TM_STAGES * TM_BOX_FLOATS * 4);      // [SP_ZW][128]
+  uint32_t* wstage = reinterpret_cast<uint32_t*>(base + (size_t)TM_STAGES * TM_BOX_FLOATS * 4);      // [ZW][128]
   // y-major task order: rows complete one after the other while the kernel runs (the counting warps follow them)
   const int xseg = (int)(task % nxseg);
   const long long t2 = task / nxseg;
   const int zc = (int)(t2 % nzc);
   const int y = (int)(t2 / nzc);
-  const int x0 = xseg * SP_XSEG, z0 = zc * SP_ZW * 32;
+  const int x0 = xseg * SP_XSEG, z0 = zc * ZW * 32;
   // boxes of this task that contain at least one valid z-plane
-  const int nbox = min(TM_BOXES, (nz - z0 + TM_BZ - 1) / TM_BZ);
+  const int nbox = min(NBOXES, (nz - z0 + TM_BZ - 1) / TM_BZ);
 
   if (lane == 0) {
     for (int s = 0; s < TM_STAGES; ++s) mbar_init(&full[wib][s], 1);
@@ -201,7 +211,7 @@ signpack_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t* __restri
   __syncwarp();
 
   uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-  for (int b = 0; b < TM_BOXES; ++b) {
+  for (int b = 0; b < NBOXES; ++b) {
     const int s = b % TM_STAGES;
     if (b < nbox) {
       mbar_wait(&full[wib][s], (uint32_t)((b / TM_STAGES) & 1));
@@ -227,21 +237,21 @@ signpack_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t* __restri
       if (lane == 0) atomicAdd(&cta_prog, 1);
     }
   }
-  // write-out, identical to signpack_kernel<true>: column j of this lane, SP_ZW words as 16-byte stores
-  uint4 r[SP_ZW];
+  // write-out, identical to signpack_kernel<true>: column j of this lane, ZW words as 16-byte stores
+  uint4 r[ZW];
 #pragma unroll
-  for (int zw = 0; zw < SP_ZW; ++zw) r[zw] = *reinterpret_cast<const uint4*>(&wstage[zw * SP_XSEG + lane * 4]);
-  const int wofs = zc * SP_ZW;
+  for (int zw = 0; zw < ZW; ++zw) r[zw] = *reinterpret_cast<const uint4*>(&wstage[zw * SP_XSEG + lane * 4]);
+  const int wofs = zc * ZW;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int x = x0 + lane * 4 + j;
     if (x < nx) {
       uint32_t* dst = bits + ((long long)x * ny + y) * W + wofs;
-      uint32_t c[SP_ZW];
+      uint32_t c[ZW];
 #pragma unroll
-      for (int zw = 0; zw < SP_ZW; ++zw) c[zw] = j == 0 ? r[zw].x : j == 1 ? r[zw].y : j == 2 ? r[zw].z : r[zw].w;
+      for (int zw = 0; zw < ZW; ++zw) c[zw] = j == 0 ? r[zw].x : j == 1 ? r[zw].y : j == 2 ? r[zw].z : r[zw].w;
 #pragma unroll
-      for (int c4 = 0; c4 < SP_ZW; c4 += 4)
+      for (int c4 = 0; c4 < ZW; c4 += 4)
         if (wofs + c4 < W) *reinterpret_cast<uint4*>(dst + c4) = make_uint4(c[c4], c[c4 + 1], c[c4 + 2], c[c4 + 3]);
     }
   }

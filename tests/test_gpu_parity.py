@@ -708,6 +708,30 @@ def test_tma_classify_parity_shapes(pkg, oracle, tma_handle, algo, shape):
 
 
 @pytest.mark.parametrize("algo", ["MC", "MT"])
+def test_counting_warps_on_ragged_shapes(pkg, oracle, monkeypatch, algo):
+    """The count riding in the TMA classify kernel (both algorithms) on ragged shapes small enough for the oracle: a fresh
+    handle with the ride's minimum task count lowered to 1; the shapes have several waves of classify CTAs (more than
+    1184 tasks), so that rows complete while the kernel runs and the counting warps do count."""
+    monkeypatch.setenv("B200ISO_TMA", "1")
+    monkeypatch.setenv("B200ISO_RIDE_MIN_TASKS", "1")
+    h = pkg.capi.Handle(0)
+    m = _method(pkg, algo, 0.0, True)
+    p = pkg.api.make_params(m)
+    for s in (pkg.synth.gyroid((129, 700, 1030)), pkg.synth.noise((129, 1300, 70), seed=5), pkg.synth.gyroid((260, 33, 97))):
+        vo, fo = oracle.isosurface(s, ALGOS[algo], iso=0.0, iso_is_f32=True, eps_is_f32=True)
+        big = s.shape[1] > 100
+        for rep in range(2):  # (the second call reuses the queues the scan kernel reset)
+            nv, nf, _ = h.count(p, s.ctypes.data, pkg.capi.HOST, *s.shape, s.shape[0])
+            assert h.classify_path() == pkg.capi.CLASSIFY_TMA
+            assert (nv, nf) == (len(vo), len(fo))
+            v, f = np.empty((nv, 3), np.float32), np.empty((nf, 3), np.int64)
+            h.generate(v.ctypes.data, f.ctypes.data, pkg.capi.HOST, 0)
+            assert np.array_equal(f, fo) and _bits_equal(v, vo)
+            assert h.ride_claimed() > 0 or not big  # the counting warps did count generate blocks
+    del h
+
+
+@pytest.mark.parametrize("algo", ["MC", "MT"])
 def test_tma_classify_nan_inf_and_float64_iso(pkg, oracle, tma_handle, algo):
     s = pkg.synth.gyroid((70, 50, 90)).copy(order="F")
     s[3, 4, 5] = np.nan
