@@ -96,10 +96,12 @@ int b200iso_use_own_stream(b200iso_handle* h);
 enum { B200ISO_CLASSIFY_LDG128 = 0, B200ISO_CLASSIFY_TMA = 1, B200ISO_CLASSIFY_SCALAR = 2, B200ISO_CLASSIFY_F64 = 3 };
 int b200iso_set_classify_mode(b200iso_handle* h, int mode);
 int b200iso_classify_path(b200iso_handle* h);
-/* Marching Cubes on the TMA classify path: every classify CTA carries `warps` extra warps that count the generate
- * blocks from the finished rows of the bit-field while the field still streams (the classify kernel is bound by HBM
- * and leaves most issue slots idle); the count kernel behind it only takes what they did not get to.  0 switches
- * this off (count kernel only), default 4, at most 8; results are identical.  Environment: B200ISO_RIDE=<warps>.
+/* On the TMA classify path every classify CTA carries `warps` extra warps that count the generate blocks (Marching
+ * Cubes or Marching Tetrahedra) from the finished rows of the bit-field while the field still streams (the classify
+ * kernel is bound by HBM and leaves most issue slots idle); the count kernel behind it only takes what they did not get
+ * to.  0 switches this off (count kernel only), default 6, at most 8 (6 for Marching Tetrahedra); results are identical.
+ * Environment: B200ISO_RIDE=<warps>; B200ISO_RIDE_MIN_TASKS=<n> (default 8192: smaller classify kernels end before
+ * the rows they complete can be followed) lets tests send small grids through the counting warps.
  * b200iso_ride_claimed: how many generate blocks the riding warps counted in the last count (synchronises). */
 int b200iso_set_ride_warps(b200iso_handle* h, int warps);
 int64_t b200iso_ride_claimed(b200iso_handle* h);
