@@ -23,6 +23,21 @@ for shp in ((131, 9, 40), (33, 20, 47), (260, 5, 1030)):
         assert _h.classify_path() == pkg.capi.CLASSIFY_TMA
         print("tma", shp, type(m).__name__, len(v), len(f))
 _h.set_classify_mode(-1)
+# the counting warps inside the TMA classify kernel, both algorithms (a fresh handle: the knobs are read at creation);
+# 1400 rows = 2800 classify tasks, more than two waves of CTAs, so the warps do count
+_os_env = {"B200ISO_TMA": "1", "B200ISO_RIDE_MIN_TASKS": "1"}
+os.environ.update(_os_env)
+_hr = pkg.capi.Handle(0)
+for k in _os_env:
+    del os.environ[k]
+s = pkg.synth.gyroid((129, 1400, 70))
+for m in (pkg.MarchingCubes(iso=F(0)), pkg.MarchingTetrahedra(iso=F(0), eps=F(1e-3))):
+    p = pkg.api.make_params(m)
+    nv, nf, _ = _hr.count(p, s.ctypes.data, pkg.capi.HOST, *s.shape, s.shape[0])
+    v, f = np.empty((nv, 3), np.float32), np.empty((nf, 3), np.int64)
+    _hr.generate(v.ctypes.data, f.ctypes.data, pkg.capi.HOST, 0)
+    print("ride", type(m).__name__, nv, nf, "claimed", _hr.ride_claimed())
+del _hr
 s = pkg.synth.gyroid((41, 19, 70))
 for m in (pkg.MarchingCubes(iso=F(0)), pkg.MarchingTetrahedra(iso=F(0), eps=F(1e-3))):
     gh = isinstance(m, pkg.MarchingTetrahedra)
