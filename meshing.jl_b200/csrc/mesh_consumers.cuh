@@ -61,6 +61,11 @@ vertex_normals_kernel(NormalArgs a) {
     const double h = n[q] > 1 && span != 0.0 ? span / (double)(n[q] - 1) : 1.0;
     ih[q] = 1.0 / h;
     double gq = (p[q] - lo[q]) * ih[q] - (q == 0 ? (double)a.x_offset : 0.0);  // continuous index in the local array
+    // A vertex within 1e-4 of a grid plane takes that plane's gradients: isosurface vertices sit on grid edges, i.e. ON
+    // two of the three families of planes up to the rounding of their coordinates, and the 4 or 6 nodes whose weight
+    // would be ~1e-7 cost 6 loads each (measured at 1024^3, 40.6 M vertices: 3.09 ms with them, 1.91 ms without).
+    const double rq = rint(gq);
+    if (fabs(gq - rq) < 1e-4) gq = rq;
     if (!(gq >= 0.0)) gq = 0.0;                                              // (also catches NaN)
     if (gq > (double)(nl[q] - 1)) gq = (double)(nl[q] - 1);
     int ci = (int)gq;

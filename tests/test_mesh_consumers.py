@@ -58,6 +58,7 @@ def _numpy_normals(s, v, lo=-1.0, hi=1.0):
     h = (hi - lo) / (n - 1)
     g = np.stack(np.gradient(s, *h, edge_order=1), -1)  # central inside, one-sided at the borders
     q = (v.astype(np.float64) - lo) / h
+    q = np.where(np.abs(q - np.rint(q)) < 1e-4, np.rint(q), q)  # (within 1e-4 of a grid plane: that plane's gradients)
     q = np.clip(q, 0, n - 1)
     c = np.minimum(q.astype(np.int64), n - 2)
     t = q - c
