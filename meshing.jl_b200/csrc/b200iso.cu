@@ -113,7 +113,10 @@ struct b200iso_handle {
   DevBuf<unsigned int> ride;
   long long ride_ny = -1, ride_tpr = -1, ride_nbi = -1;  // shape the cumulative row counters belong to
   unsigned int ride_step = 0;
-  long long ride_min_tasks = 8192;  // counting warps ride only in classify kernels of at least this many tasks (env B200ISO_RIDE_MIN_TASKS: tests)
+  // counting warps ride only in classify kernels of at least this many tasks (env B200ISO_RIDE_MIN_TASKS: tests).  Measured on
+  // x-slabs of the 1024^3 gyroid (profiles/r2_tail_and_small_slab.txt): 257 planes (6144 tasks) 0.443 -> 0.427 ms per step with
+  // 4 warps (0.433 with 6); 129 planes (4096 tasks) 0.263 -> 0.268: the rows complete too late for the warps to get much done.
+  long long ride_min_tasks = 6144;
   int ride_stop = iso::TM_WARPS * iso::SP_ZW * 3 / 4;  // counting warps stop claiming at 3/4 of the CTA's classify work (env B200ISO_RIDE_STOP: z-words of 64)
   int ride_warps = 6;  // counting warps per TMA classify CTA (0 = separate count kernel only; b200iso_set_ride_warps, env B200ISO_RIDE)
   // grid coordinates are a function of the call's shape and ranges only: recomputed when those change
@@ -289,12 +292,13 @@ int enqueue_count(b200iso_handle* h, const b200iso_params* p, const void* sdf_de
         cr.celloff = mt ? h->celloff.p : nullptr;
         ride = true;
       }
+      const int rw = ntasks < 8192 ? std::min(h->ride_warps, 4) : h->ride_warps;  // (short kernels: fewer counting warps, see ride_min_tasks)
       const unsigned tb = (unsigned)((ntasks + iso::TM_WARPS - 1) / iso::TM_WARPS);
       if (mt && ride)
-        iso::signpack_tma_kernel<true><<<tb, (iso::TM_WARPS + std::min(h->ride_warps, iso::TM_CNT_WARPS_MT)) * 32, iso::TM_SMEM, st>>>(
+        iso::signpack_tma_kernel<true><<<tb, (iso::TM_WARPS + std::min(rw, iso::TM_CNT_WARPS_MT)) * 32, iso::TM_SMEM, st>>>(
             tmap, h->bits.p, g.nx, g.ny, g.nz, g.W, thr, nxseg, nzc, ntasks, h->chain.p, nclear, cr);
       else
-        iso::signpack_tma_kernel<false><<<tb, (iso::TM_WARPS + (ride ? h->ride_warps : 0)) * 32, iso::TM_SMEM, st>>>(
+        iso::signpack_tma_kernel<false><<<tb, (iso::TM_WARPS + (ride ? rw : 0)) * 32, iso::TM_SMEM, st>>>(
             tmap, h->bits.p, g.nx, g.ny, g.nz, g.W, thr, nxseg, nzc, ntasks, h->chain.p, nclear, cr);
       h->classify_path = B200ISO_CLASSIFY_TMA;
     } else if (vec) {

@@ -11,6 +11,8 @@ if kind == "gyroid":
     t = pkg.synth.gyroid_torch(n, "cuda")
 elif kind == "gyroid129":  # one rank's slab of the 1024^3 volume split over 8 GPUs
     t = pkg.synth.gyroid_torch(n, "cuda", x_slice=(0, n // 8 + 1), ldx=n // 8 + 4)
+elif kind == "gyroid257":  # one rank's slab of the 1024^3 volume split over 4 GPUs (also a slab of the host pipeline)
+    t = pkg.synth.gyroid_torch(n, "cuda", x_slice=(0, n // 4 + 1), ldx=n // 4 + 4)
 else:  # rank 3's slab of the 2048^3 multi-sphere/torus volume split over 8 GPUs
     t = pkg.synth.multisphere_torus((n, n, n), x_slice=(3 * n // 8, 4 * n // 8 + 1), xp=torch, device="cuda", ldx=n // 8 + 4)
 nx = t.shape[0]
