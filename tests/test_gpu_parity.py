@@ -849,3 +849,46 @@ def test_full_size_1024_gyroid_mt_against_oracle_ranges(pkg, oracle):
         # vertices of the ghost plane keep their relative order
         gh = ~own
         assert np.array_equal(np.argsort(fg[gh], kind="stable"), np.argsort(of_r[gh], kind="stable"))
+
+
+# ---- randomised sweep (hypothesis, derandomised: the same examples every run) ---------------------------------------
+def _random_field(shape, kind, seed, f64):
+    rng = np.random.default_rng(seed)
+    if kind == 0:  # smooth: a sum of a few random plane waves (a surface-like level set)
+        x, y, z = np.meshgrid(*[np.linspace(0, 1, n) for n in shape], indexing="ij")
+        s = np.zeros(shape)
+        for _ in range(3):
+            k = rng.uniform(-9, 9, 3)
+            s += rng.uniform(0.3, 1.0) * np.sin(k[0] * x + k[1] * y + k[2] * z + rng.uniform(0, 6.28))
+    elif kind == 1:  # dense noise
+        s = rng.uniform(-1, 1, shape)
+    else:  # few distinct values: many samples EQUAL to the level and to each other (degenerate interpolation)
+        s = rng.integers(-2, 3, shape).astype(np.float64) * 0.25
+    s = s.astype(np.float64 if f64 else np.float32)
+    if seed % 5 == 0:  # a few NaN / Inf samples
+        idx = tuple(rng.integers(0, n, 6) for n in shape)
+        s[idx] = np.array([np.nan, np.inf, -np.inf, np.nan, np.inf, -np.inf], dtype=s.dtype)
+    return np.asfortranarray(s)
+
+
+try:
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @pytest.mark.gpu
+    @settings(max_examples=400, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(nx=st.integers(2, 45), ny=st.integers(2, 30), nz=st.sampled_from([2, 3, 17, 32, 33, 64, 100, 129, 260]), kind=st.integers(0, 2),
+           seed=st.integers(0, 10 ** 6), algo=st.sampled_from(["MC", "MT"]), f32=st.booleans(), f64_field=st.booleans(),
+           rk=st.integers(0, 2), iso=st.sampled_from([0.0, 0.25, -0.25, 0.1, 0.5]), tma=st.booleans())
+    def test_random_fields_against_the_oracle(pkg, oracle, nx, ny, nz, kind, seed, algo, f32, f64_field, rk, iso, tma):
+        """Random shapes, field kinds (smooth / noise / few distinct values with samples equal to the level; NaN and Inf
+        sprinkled in), level, method and range types, field precision, both classify kernels: bit-exact against the oracle."""
+        s = _random_field((nx, ny, nz), kind, seed, f64_field)
+        ranges = ((-1, 1), (0, 3), (-2, 5)) if rk == 0 else ((-1.0, 1.5), (0.25, 3.0), (-2.0, 5.5))
+        h = pkg.api.get_handle(0)
+        h.set_classify_mode(1 if tma else -1)
+        try:
+            _check(pkg, oracle, s, algo, iso=iso, f32=f32, ranges=ranges, rk=rk)
+        finally:
+            h.set_classify_mode(-1)
+except ImportError:  # hypothesis missing: the parametrised tests above stand alone
+    pass
