@@ -303,6 +303,8 @@ struct Downloader {
   cudaError_t start(Pool* p, int max_jobs, bool dst_pinned, cudaEvent_t after) {
     pool = p, pinned = dst_pinned;
     T = pinned ? 1 : std::max(1, default_threads() / 2);
+    if (const char* e = getenv("B200ISO_HOST_DOWN_THREADS"))
+      if (!pinned) T = std::max(1, std::min(64, atoi(e)));
     if (cudaError_t e = pool->ensure(pool->out, T, max_jobs, !pinned)) return e;
     jobs.assign(max_jobs, Job{});
     drained = std::vector<std::atomic<int>>(T);
