@@ -99,8 +99,9 @@ int b200iso_classify_path(b200iso_handle* h);
 /* On the TMA classify path every classify CTA carries `warps` extra warps that count the generate blocks (Marching
  * Cubes or Marching Tetrahedra) from the finished rows of the bit-field while the field still streams (the classify
  * kernel is bound by HBM and leaves most issue slots idle); the count kernel behind it only takes what they did not get
- * to.  0 switches this off (count kernel only), default 6, at most 8 (6 for Marching Tetrahedra); results are identical.
- * Environment: B200ISO_RIDE=<warps>; B200ISO_RIDE_MIN_TASKS=<n> (default 8192: smaller classify kernels end before
+ * to.  0 switches this off (count kernel only), default 6, at most 8 (6 for Marching Tetrahedra; 4 are used on classify
+ * kernels of fewer than 8192 tasks); results are identical.
+ * Environment: B200ISO_RIDE=<warps>; B200ISO_RIDE_MIN_TASKS=<n> (default 6144: smaller classify kernels end before
  * the rows they complete can be followed) lets tests send small grids through the counting warps.
  * b200iso_ride_claimed: how many generate blocks the riding warps counted in the last count (synchronises). */
 int b200iso_set_ride_warps(b200iso_handle* h, int warps);
